@@ -1,0 +1,166 @@
+/* xyk.h -- C ABI of the B200-native Kuramoto-XY exact-statevector engine.
+ *
+ * Drop-in boundary for the reference's statevector route
+ *   auto_solve -> QuantumKuramotoSolver(n, K, omega).run(t_max, dt, trotter_per_step)
+ * (reference: src/scpn_quantum_control/phase/backend_selector.py:288-293,
+ *  src/scpn_quantum_control/phase/xy_kuramoto.py:86-258).  Each entry point below names the
+ * reference interface it replaces.  Plain pointers and sizes only: no torch / numpy types.
+ *
+ * Conventions
+ *   - qubit q <-> bit q of the basis index (little endian), amplitudes interleaved (re, im).
+ *   - dtype 0 = complex128 (double re, im), dtype 1 = complex64 (float re, im).
+ *   - K is row-major double[n*n], omega is double[n]; the library symmetrises K as (K+K^T)/2,
+ *     ignores its diagonal and drops |K_ij| < 1e-15, |omega_i| <= 1e-15 exactly like
+ *     bridge/knm_hamiltonian.py:172-195.  All *validation* with the reference's error
+ *     messages is done by the Python host layer before calling in.
+ *   - every function returns 0 on success; a non-zero status has a message retrievable with
+ *     xyk_last_error(handle) (or xyk_last_error(NULL) for failures of xyk_create).
+ *   - a handle is not thread safe; all work is enqueued on a handle-owned CUDA stream and the
+ *     calls that return host data synchronise that stream.
+ *   - caller owns every host buffer for the duration of the call; the library owns device
+ *     state inside the handle.
+ */
+#ifndef XYK_H_
+#define XYK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xyk_handle_s *xyk_handle;
+
+/* status codes */
+#define XYK_OK 0
+#define XYK_ERR_INVALID 1     /* bad argument                                   */
+#define XYK_ERR_CUDA 2        /* CUDA runtime failure                           */
+#define XYK_ERR_NOMEM 3       /* device allocation failed (maps to MemoryError) */
+#define XYK_ERR_STATE 4       /* call sequence error (e.g. no problem set)      */
+#define XYK_ERR_UNSUPPORTED 5 /* configuration not supported by this build      */
+#define XYK_NEED_EXCHANGE 100 /* sharded run: host must perform the all-to-all  */
+
+/* engines (xyk_set_option(h, XYK_OPT_ENGINE, v)) */
+#define XYK_ENGINE_AUTO 0   /* tiled for n_local >= 13, gate-by-gate below          */
+#define XYK_ENGINE_SIMPLE 1 /* one kernel per gate, canonical layout                */
+#define XYK_ENGINE_TILED 2  /* fused cache-blocked passes (shared-memory tiles)     */
+
+#define XYK_OPT_ENGINE 1
+#define XYK_OPT_FUSE_PHASE 2   /* 1 (default): Z phase folded into the first pass of a layer */
+#define XYK_OPT_TILED_OBS 3    /* 1 (default): tile-based observable sweeps                  */
+
+int xyk_version(void);
+const char *xyk_last_error(xyk_handle h);
+int xyk_device_count(int *count);
+/* free / total bytes of device `device` */
+int xyk_device_memory(int device, size_t *free_bytes, size_t *total_bytes);
+
+/* Create an engine for n_qubits on CUDA device `device`.
+ * world_size / rank: 1 / 0 for a single GPU.  For a sharded state (world_size = 2,4,8) this
+ * handle owns the amplitudes whose top log2(world_size) *physical* index bits equal `rank`.
+ * Replaces: QuantumKuramotoSolver.__init__ state ownership (xy_kuramoto.py:86-106) and the
+ * dense budget gate's allocation (dense_budget.py:141-172; budget is checked by the host). */
+int xyk_create(int n_qubits, int dtype, int device, int world_size, int rank, xyk_handle *out);
+int xyk_destroy(xyk_handle h);
+int xyk_set_option(xyk_handle h, int option, int64_t value);
+
+/* Build the ordered, thresholded term list (gate order) from (K, omega).
+ * Replaces: knm_to_hamiltonian / knm_to_xxz_hamiltonian(delta=0)
+ * (bridge/knm_hamiltonian.py:141-217).  May be called again at any time to re-parameterise
+ * the couplings without touching the state (control/realtime_feedback.py:98-137). */
+int xyk_set_problem(xyk_handle h, const double *K, const double *omega);
+/* number of retained pair terms / Z terms of the current problem */
+int xyk_term_counts(xyk_handle h, int *n_pairs, int *n_z);
+
+/* psi0 = prod_i Ry(omega_i mod 2pi)|0>, generated on the device.
+ * Replaces: xy_kuramoto.py:236-242 (Statevector.from_instruction of the Ry circuit). */
+int xyk_init_product_state(xyk_handle h);
+
+/* Evolve one grid interval `delta` with `reps` repetitions of the product formula of `order`:
+ *   order 1 = LieTrotter, 2 = SuzukiTrotter(order=2) (Qiskit term order), 4 / 6 = Suzuki
+ *   compositions of the order-2 layer (the route to the exact per-step propagation the
+ *   reference's run() numerically returns).
+ * Replaces: sv.evolve(solver.evolve(step_dt, trotter_per_step))  (xy_kuramoto.py:132-154,246-247).
+ * Sharded handles may return XYK_NEED_EXCHANGE: the host then performs the all-to-all
+ * described by xyk_exchange_info(), calls xyk_exchange_done() and calls xyk_continue(). */
+int xyk_apply_layers(xyk_handle h, double delta, int order, int reps);
+int xyk_continue(xyk_handle h);
+/* all-to-all description: send `src`, receive into `dst`; both hold 2^n_local amplitudes split
+ * in world_size equal contiguous blocks (block s goes to / comes from rank s). */
+int xyk_exchange_info(xyk_handle h, void **src, void **dst, size_t *bytes_per_block);
+int xyk_exchange_done(xyk_handle h);
+
+/* <X_q>, <Y_q> for every qubit (partial sums over this shard for sharded handles: the host
+ * adds the per-rank arrays).  Qubits that are currently global on a sharded handle are
+ * reported through need_exchange != 0 (see python host).
+ * Replaces: scpn_quantum_engine.all_xy_expectations (scpn_quantum_engine/src/pauli.rs:180-214). */
+int xyk_xy_expectations(xyk_handle h, double *exp_x, double *exp_y);
+/* R = |sum_q (<X_q> + i<Y_q>)| / n, psi = arg.  Replaces: measure_order_parameter
+ * (xy_kuramoto.py:156-185), state_order_param_sparse (pauli.rs:72-116),
+ * order_param_from_statevector (sectors.rs:67-99).  Single-GPU handles only. */
+int xyk_order_parameter(xyk_handle h, double *R, double *psi);
+/* <Z_q> for every qubit.  Replaces: expectation_pauli_fast(.., pauli=2) (pauli.rs:122-173). */
+int xyk_z_expectations(xyk_handle h, double *exp_z);
+/* C_ij = <X_iX_j + Y_iY_j>, row-major double[n*n].  Replaces: correlation_matrix_xy
+ * (scpn_quantum_engine/src/sectors.rs:105-145).  Single-GPU handles only. */
+int xyk_correlation_matrix_xy(xyk_handle h, double *C);
+/* <H> = -sum K_ij C_ij - sum omega_i <Z_i>.  Replaces: energy_expectation (xy_kuramoto.py:260-264). */
+int xyk_energy(xyk_handle h, double *E);
+/* sum_k |psi_k|^2 over this shard */
+int xyk_norm2(xyk_handle h, double *norm2);
+
+/* The whole run() loop on the device: init, R[0], then for each step_sizes[s]: evolve, R[s+1].
+ * Replaces: QuantumKuramotoSolver.run hot loop (xy_kuramoto.py:236-248). Single GPU only. */
+int xyk_run(xyk_handle h, const double *step_sizes, int m, int reps, int order, double *R_out);
+
+/* Copy the state out / in, in canonical (logical) index order.
+ * is_device = 0: dst/src are host pointers; 1: device pointers on the handle's device.
+ * dst/src hold 2^n_local amplitudes of the handle's dtype.  Sharded handles must be in the
+ * canonical layout (use xyk_canonicalise first; may require exchanges).
+ * Replaces: np.asarray(sv.data) (xy_kuramoto.py:167) / Statevector(data). */
+int xyk_get_state(xyk_handle h, void *dst, int is_device);
+int xyk_set_state(xyk_handle h, const void *src, int is_device);
+/* raw access for zero-copy wrappers (torch tensors as buffers): current buffer, physical layout */
+int xyk_state_buffer(xyk_handle h, void **ptr, size_t *bytes);
+/* perm[q] = physical bit position of logical qubit q (length n_qubits) */
+int xyk_get_layout(xyk_handle h, int *perm);
+int xyk_canonicalise(xyk_handle h);
+int xyk_synchronize(xyk_handle h);
+/* the CUDA stream work is enqueued on (cudaStream_t as void*) */
+int xyk_stream(xyk_handle h, void **stream);
+
+/* Introspection for benchmarks / tests. */
+typedef struct {
+    int64_t kernel_launches; /* kernels launched by this handle since creation             */
+    int64_t pass_launches;   /* of which fused tile passes                                 */
+    int64_t state_sweeps;    /* read+write sweeps over the state issued by apply_layers    */
+    int32_t last_passes;     /* tile passes of the last apply_layers call                  */
+    int32_t last_rounds;     /* register rounds of the last apply_layers call              */
+    int32_t last_gates;      /* pair gates of the last apply_layers call                   */
+    int32_t last_layers1;    /* first-order-layer equivalents of the last apply_layers     */
+    float last_pass_ms;      /* CUDA-event time of the passes of the last call (if timing) */
+    int32_t timing_enabled;
+} xyk_stats;
+int xyk_get_stats(xyk_handle h, xyk_stats *out);
+int xyk_enable_timing(xyk_handle h, int on);
+
+/* Schedule compiler, host only (no device needed): writes a JSON description of the pass
+ * program for `reps` repetitions of `order` on an n-qubit all-to-all (or given K) problem.
+ * Returns the number of bytes required (including NUL); fills buf if cap is large enough. */
+int64_t xyk_plan_describe(int n_local, int dtype, const double *K, const double *omega, int n,
+                          double delta, int order, int reps, char *buf, int64_t cap);
+
+/* Batched parameter sweep: B independent n-qubit (n <= 12) problems evolved concurrently,
+ * one CTA per problem with the whole state in shared memory.
+ *   K: double[B*n*n], omega: double[B*n], step_sizes: double[m] (shared grid),
+ *   R_out: double[B*(m+1)], final_states: NULL or B*2^n amplitudes (host, complex128).
+ * Replaces: a Python loop of QuantumKuramotoSolver(n, K_b, omega_b).run(...) (config 3). */
+int xyk_batch_run(int device, int n, int B, const double *K, const double *omega,
+                  const double *step_sizes, int m, int reps, int order, double *R_out,
+                  void *final_states);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XYK_H_ */

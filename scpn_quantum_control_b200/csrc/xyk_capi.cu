@@ -1,0 +1,834 @@
+// C ABI (include/xyk.h) of the B200-native Kuramoto-XY statevector engine.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/xyk.h"
+#include "xyk_internal.h"
+#include "xyk_kernels.cuh"
+#include "xyk_small.cuh"
+
+using namespace xyk;
+
+namespace {
+
+constexpr int kTB = 12;  // complex128 tile: 2^12 amplitudes = 64 KiB of shared memory
+constexpr int kRB = 5;   // 32 amplitudes (128 registers) per thread
+using Desc = PassDesc<kTB, kRB>;
+static_assert(sizeof(Desc) <= 4000, "pass descriptor must fit the classic 4 KB kernel-parameter space");
+
+thread_local std::string g_global_error;
+
+struct Program {
+    Plan plan;
+    std::vector<Desc> descs;        // one per pass
+    std::vector<char> lift;         // shear form allowed for the pass
+};
+
+}  // namespace
+
+struct xyk_handle_s {
+    int n = 0, nlocal = 0, world = 1, rank = 0, gbits = 0, dtype = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    void* buf[2] = {nullptr, nullptr};
+    size_t bytes = 0;
+    int cur = 0;
+    std::vector<int> perm;  // logical qubit -> physical bit (>= nlocal: sharded over ranks)
+    bool have_problem = false, state_valid = false;
+    std::vector<double> Ksym, omega;
+    std::vector<PairTerm> pairs;
+    std::vector<ZTerm> zterms;
+    uint64_t problem_version = 0;
+    int engine_opt = XYK_ENGINE_AUTO;
+    int fuse_phase = 1;
+    int tiled_obs = 1;
+    int sm_count = 148;
+    int pass_grid = 0;
+    // scratch
+    double2* d_tab = nullptr;     // 3 x 2^11 phase tables
+    double* d_partial = nullptr;  // reduction partials
+    double* d_out = nullptr;      // reduced values
+    double* h_out = nullptr;      // pinned staging
+    std::map<std::tuple<uint64_t, int, int, double>, std::shared_ptr<Program>> programs;
+    xyk_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+};
+
+namespace {
+
+constexpr int kTabStride = 2048;
+constexpr int kRedBlocks = 1184;  // 8 x 148
+constexpr int kPartialDoubles = kRedBlocks * (kMaxQ + 1) * 2;
+
+int fail(xyk_handle h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    else g_global_error = msg;
+    return code;
+}
+
+#define XYK_CUDA(h, expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            const bool oom__ = (e__ == cudaErrorMemoryAllocation);                             \
+            return fail(h, oom__ ? XYK_ERR_NOMEM : XYK_ERR_CUDA,                               \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+        }                                                                                      \
+    } while (0)
+
+#define XYK_CHECK(h, cond, code, msg) \
+    do {                              \
+        if (!(cond)) return fail(h, code, msg); \
+    } while (0)
+
+size_t amp_bytes(int dtype) { return dtype == 0 ? 16 : 8; }
+
+int grid_for(xyk_handle h, uint64_t items, int block) {
+    const uint64_t want = (items + block - 1) / block;
+    const uint64_t cap = (uint64_t)h->sm_count * 16;
+    return (int)std::max<uint64_t>(1, std::min(want, cap));
+}
+
+int ensure_alt(xyk_handle h) {
+    if (h->buf[1]) return XYK_OK;
+    XYK_CUDA(h, cudaMalloc(&h->buf[1], h->bytes));
+    return XYK_OK;
+}
+
+bool perm_is_identity(xyk_handle h) {
+    for (int q = 0; q < h->n; ++q)
+        if (h->perm[q] != q) return false;
+    return true;
+}
+
+template <typename real>
+int launch_init(xyk_handle h) {
+    QubitTable T{};
+    T.nq = h->n;
+    T.nlocal = h->nlocal;
+    T.rank = h->rank;
+    const double two_pi = 2.0 * M_PI;
+    for (int q = 0; q < h->n; ++q) {
+        double a = std::fmod(h->omega[q], two_pi);  // Python's % : result has the sign of the modulus
+        if (a < 0.0) a += two_pi;
+        T.c[q] = std::cos(a / 2.0);
+        T.s[q] = std::sin(a / 2.0);
+        T.pos[q] = (uint8_t)h->perm[q];
+    }
+    using C = typename cplx<real>::type;
+    const uint64_t dim = 1ull << h->nlocal;
+    init_product_kernel<real><<<grid_for(h, dim, 256), 256, 0, h->stream>>>((C*)h->buf[h->cur], T);
+    h->stats.kernel_launches++;
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
+// diagonal phase exp(+i tau sum_q omega_q (1-2 b_q)) in the current layout (gate-by-gate path)
+int apply_phase(xyk_handle h, double tau) {
+    if (h->zterms.empty() || tau == 0.0) return XYK_OK;
+    PhaseSpec S{};
+    S.nbits = h->n;
+    S.nlocal = h->nlocal;
+    S.rank = h->rank;
+    S.tau = tau;
+    for (int b = 0; b < kMaxQ; ++b) S.w[b] = 0.0;
+    for (const auto& z : h->zterms) S.w[h->perm[z.i]] = z.w;
+    const int nl = h->nlocal;
+    S.b1 = std::min(nl, 11);
+    S.b2 = std::min(nl, 22);
+    if (nl - S.b2 > 11) {  // spread three chunks evenly for very large shards
+        S.b1 = (nl + 2) / 3;
+        S.b2 = S.b1 + (nl - S.b1 + 1) / 2;
+    }
+    XYK_CHECK(h, S.b1 <= 11 && S.b2 - S.b1 <= 11 && nl - S.b2 <= 11, XYK_ERR_UNSUPPORTED,
+              "phase tables support at most 33 local qubits");
+    phase_table_kernel<<<dim3(8, 3), 256, 0, h->stream>>>(h->d_tab, S, kTabStride);
+    const uint64_t dim = 1ull << nl;
+    if (h->dtype == 0)
+        phase_apply_kernel<double><<<grid_for(h, dim, 256), 256, 0, h->stream>>>(
+            (double2*)h->buf[h->cur], h->d_tab, kTabStride, nl, S.b1, S.b2);
+    else
+        phase_apply_kernel<float><<<grid_for(h, dim, 256), 256, 0, h->stream>>>(
+            (float2*)h->buf[h->cur], h->d_tab, kTabStride, nl, S.b1, S.b2);
+    h->stats.kernel_launches += 2;
+    h->stats.state_sweeps += 1;
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
+int apply_pair_simple(xyk_handle h, int i, int j, double phi) {
+    const int pi = h->perm[i], pj = h->perm[j];
+    XYK_CHECK(h, pi < h->nlocal && pj < h->nlocal, XYK_ERR_UNSUPPORTED,
+              "gate-by-gate engine cannot touch a sharded (global) qubit");
+    const double c = std::cos(phi), s = std::sin(phi);
+    const uint64_t quarter = 1ull << (h->nlocal - 2);
+    if (h->dtype == 0)
+        pair_gate_kernel<double><<<grid_for(h, quarter, 256), 256, 0, h->stream>>>((double2*)h->buf[h->cur],
+                                                                                 h->nlocal, pi, pj, c, s);
+    else
+        pair_gate_kernel<float><<<grid_for(h, quarter, 256), 256, 0, h->stream>>>((float2*)h->buf[h->cur],
+                                                                                h->nlocal, pi, pj, c, s);
+    h->stats.kernel_launches++;
+    h->stats.state_sweeps++;
+    return XYK_OK;
+}
+
+int run_segments_simple(xyk_handle h, const std::vector<Segment>& segs) {
+    for (const auto& s : segs) {
+        int rc = apply_phase(h, s.ztau);
+        if (rc) return rc;
+        for (const auto& g : s.gates) {
+            rc = apply_pair_simple(h, g.i, g.j, g.phi);
+            if (rc) return rc;
+        }
+    }
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
+// permute the state so that logical qubit q sits on physical bit target[q]
+int relayout(xyk_handle h, const std::vector<int>& target) {
+    bool same = true;
+    for (int q = 0; q < h->n; ++q) same &= (h->perm[q] == target[q]);
+    if (same) return XYK_OK;
+    PermSpec S{};
+    S.nlocal = h->nlocal;
+    for (int b = 0; b < kMaxQ; ++b) S.dst_of_src[b] = (uint8_t)b;
+    for (int q = 0; q < h->n; ++q) {
+        XYK_CHECK(h, (h->perm[q] < h->nlocal) == (target[q] < h->nlocal) &&
+                         (h->perm[q] < h->nlocal || h->perm[q] == target[q]),
+                  XYK_ERR_UNSUPPORTED, "relayout cannot move sharded qubits");
+        if (h->perm[q] < h->nlocal) S.dst_of_src[h->perm[q]] = (uint8_t)target[q];
+    }
+    int rc = ensure_alt(h);
+    if (rc) return rc;
+    const uint64_t dim = 1ull << h->nlocal;
+    if (h->dtype == 0)
+        permute_kernel<double><<<grid_for(h, dim, 256), 256, 0, h->stream>>>(
+            (const double2*)h->buf[h->cur], (double2*)h->buf[h->cur ^ 1], S);
+    else
+        permute_kernel<float><<<grid_for(h, dim, 256), 256, 0, h->stream>>>(
+            (const float2*)h->buf[h->cur], (float2*)h->buf[h->cur ^ 1], S);
+    h->stats.kernel_launches++;
+    h->stats.state_sweeps++;
+    XYK_CUDA(h, cudaGetLastError());
+    h->cur ^= 1;
+    h->perm = target;
+    return XYK_OK;
+}
+
+void fill_desc(const Plan& plan, const PlanPass& pp, Desc& d, bool& lift_ok) {
+    std::memset(&d, 0, sizeof(d));
+    d.nq = plan.nq;
+    d.nrounds = (int)pp.rounds.size();
+    d.has_phase = 0;
+    for (int b = 0; b + kTB < plan.nq; ++b) d.hi_out[b] = (uint8_t)pp.out_of_in[kTB + b];
+    // tile bits ordered by their output position
+    int order[kTB];
+    for (int k = 0; k < kTB; ++k) order[k] = k;
+    std::sort(order, order + kTB, [&](int a, int b) { return pp.out_of_in[a] < pp.out_of_in[b]; });
+    for (int m = 0; m < kTB; ++m) {
+        d.st_lsrc[m] = (uint8_t)order[m];
+        d.st_odst[m] = (uint8_t)pp.out_of_in[order[m]];
+    }
+    lift_ok = true;
+    for (int r = 0; r < d.nrounds; ++r) {
+        const PlanRound& pr = pp.rounds[r];
+        for (int s = 0; s < Desc::NSLOT; ++s)
+            if ((pr.mask >> s) & 1u) {
+                const double phi = std::remainder(pr.phi[s], 2.0 * M_PI);
+                if (std::fabs(phi) > 1.5) lift_ok = false;
+            }
+    }
+    for (int r = 0; r < d.nrounds; ++r) {
+        const PlanRound& pr = pp.rounds[r];
+        Desc::Round& R = d.rounds[r];
+        for (int b = 0; b < Desc::NT; ++b) R.thrpos[b] = (uint8_t)pr.thrpos[b];
+        for (int k = 0; k < kRB; ++k) R.regpos[k] = (uint8_t)pr.regpos[k];
+        R.mask = pr.mask;
+        for (int s = 0; s < Desc::NSLOT; ++s) {
+            if (!((pr.mask >> s) & 1u)) continue;
+            const double phi = std::remainder(pr.phi[s], 2.0 * M_PI);
+            if (lift_ok) {
+                R.ca[s] = -std::tan(phi / 2.0);
+                R.cb[s] = std::sin(phi);
+            } else {
+                R.ca[s] = std::cos(phi);
+                R.cb[s] = std::sin(phi);
+            }
+        }
+    }
+}
+
+std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int reps) {
+    const auto key = std::make_tuple(h->problem_version, order, reps, delta);
+    auto it = h->programs.find(key);
+    if (it != h->programs.end()) return it->second;
+    auto prog = std::make_shared<Program>();
+    int l1 = 0;
+    std::vector<Segment> segs = build_sequence(h->pairs, delta, order, reps, &l1);
+    SchedConfig cfg;
+    cfg.TB = kTB;
+    cfg.RB = kRB;
+    cfg.max_rounds = kMaxRounds;
+    // only local qubits can be scheduled here (single-GPU: all of them)
+    prog->plan = compile_plan(h->nlocal, segs, cfg);
+    prog->plan.layers1_equiv = l1;
+    prog->descs.resize(prog->plan.passes.size());
+    prog->lift.resize(prog->plan.passes.size());
+    for (size_t p = 0; p < prog->plan.passes.size(); ++p) {
+        bool lift = true;
+        fill_desc(prog->plan, prog->plan.passes[p], prog->descs[p], lift);
+        prog->lift[p] = lift ? 1 : 0;
+    }
+    if (h->programs.size() > 64) h->programs.clear();
+    h->programs[key] = prog;
+    return prog;
+}
+
+int configure_pass_kernels(xyk_handle h) {
+    const int smem = (1 << kTB) * 16;
+    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int occ = 0;
+    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_pass_kernel<kTB, kRB, true, 3>, 1 << (kTB - kRB), smem));
+    if (occ < 1) occ = 1;
+    h->pass_grid = occ * h->sm_count;
+    return XYK_OK;
+}
+
+int run_program_tiled(xyk_handle h, Program& prog) {
+    const Plan& plan = prog.plan;
+    int rc = ensure_alt(h);
+    if (rc) return rc;
+    if (!h->pass_grid) {
+        rc = configure_pass_kernels(h);
+        if (rc) return rc;
+    }
+    if (!plan.passes.empty()) {
+        std::vector<int> target(h->perm);
+        for (int q = 0; q < plan.nq; ++q) target[q] = plan.start_perm[q];
+        rc = relayout(h, target);
+        if (rc) return rc;
+    }
+    const uint64_t ntiles = 1ull << (h->nlocal - kTB);
+    const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)h->pass_grid);
+    const int smem = (1 << kTB) * 16;
+    if (h->stats.timing_enabled) cudaEventRecord(h->ev0, h->stream);
+    for (size_t p = 0; p < plan.passes.size(); ++p) {
+        const PlanPass& pp = plan.passes[p];
+        if (pp.has_phase) {
+            rc = apply_phase(h, pp.ztau);
+            if (rc) return rc;
+        }
+        const double2* in = (const double2*)h->buf[h->cur];
+        double2* out = (double2*)h->buf[h->cur ^ 1];
+        if (prog.lift[p])
+            tile_pass_kernel<kTB, kRB, true, 3><<<grid, 1 << (kTB - kRB), smem, h->stream>>>(in, out, prog.descs[p], ntiles);
+        else
+            tile_pass_kernel<kTB, kRB, false, 3><<<grid, 1 << (kTB - kRB), smem, h->stream>>>(in, out, prog.descs[p], ntiles);
+        h->cur ^= 1;
+        std::vector<int> np(h->perm);
+        for (int q = 0; q < plan.nq; ++q) np[q] = pp.out_of_in[h->perm[q]];
+        h->perm.swap(np);
+        h->stats.kernel_launches++;
+        h->stats.pass_launches++;
+        h->stats.state_sweeps++;
+    }
+    if (plan.has_trailing_phase) {
+        rc = apply_phase(h, plan.trailing_ztau);
+        if (rc) return rc;
+    }
+    if (h->stats.timing_enabled) {
+        cudaEventRecord(h->ev1, h->stream);
+        cudaEventSynchronize(h->ev1);
+        cudaEventElapsedTime(&h->stats.last_pass_ms, h->ev0, h->ev1);
+    }
+    XYK_CUDA(h, cudaGetLastError());
+    h->stats.last_passes = (int)plan.passes.size();
+    h->stats.last_rounds = plan.total_rounds;
+    h->stats.last_gates = plan.total_gates;
+    h->stats.last_layers1 = plan.layers1_equiv;
+    return XYK_OK;
+}
+
+bool use_tiled(xyk_handle h) {
+    if (h->dtype != 0) return false;  // complex64 runs gate by gate in this build
+    if (h->engine_opt == XYK_ENGINE_SIMPLE) return false;
+    if (h->nlocal < kTB) return false;
+    if (h->engine_opt == XYK_ENGINE_TILED) return true;
+    return h->nlocal >= 13;
+}
+
+// <X_q>, <Y_q> for local qubits -> d_out[2q], d_out[2q+1] (already multiplied by 2)
+int xy_expect_device(xyk_handle h) {
+    const uint64_t half = 1ull << (h->nlocal - 1);
+    const int grid = std::min(kRedBlocks, grid_for(h, half, 256));
+    for (int q = 0; q < h->n; ++q) {
+        const int pos = h->perm[q];
+        XYK_CHECK(h, pos < h->nlocal, XYK_ERR_UNSUPPORTED, "observable on a sharded qubit needs an exchange first");
+        double2* part = (double2*)h->d_partial + (size_t)q * kRedBlocks;
+        if (h->dtype == 0)
+            xy_expect_kernel<double><<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], h->nlocal, pos, part);
+        else
+            xy_expect_kernel<float><<<grid, 256, 0, h->stream>>>((const float2*)h->buf[h->cur], h->nlocal, pos, part);
+        h->stats.kernel_launches++;
+    }
+    xy_finalize_kernel<<<h->n, 128, 0, h->stream>>>((const double2*)h->d_partial, grid, kRedBlocks, h->d_out);
+    h->stats.kernel_launches++;
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int xyk_version(void) { return 100; }
+
+const char* xyk_last_error(xyk_handle h) { return h ? h->err.c_str() : g_global_error.c_str(); }
+
+int xyk_device_count(int* count) {
+    if (!count) return XYK_ERR_INVALID;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(nullptr, XYK_ERR_CUDA, cudaGetErrorString(e));
+    }
+    return XYK_OK;
+}
+
+int xyk_device_memory(int device, size_t* free_bytes, size_t* total_bytes) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMemGetInfo(free_bytes, total_bytes);
+    if (e != cudaSuccess) return fail(nullptr, XYK_ERR_CUDA, cudaGetErrorString(e));
+    return XYK_OK;
+}
+
+int xyk_create(int n_qubits, int dtype, int device, int world_size, int rank, xyk_handle* out) {
+    if (!out) return fail(nullptr, XYK_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_qubits < 1 || n_qubits > kMaxQ) return fail(nullptr, XYK_ERR_INVALID, "n_qubits out of range");
+    if (dtype != 0 && dtype != 1) return fail(nullptr, XYK_ERR_INVALID, "dtype must be 0 (complex128) or 1 (complex64)");
+    if (world_size < 1 || (world_size & (world_size - 1)) || rank < 0 || rank >= world_size)
+        return fail(nullptr, XYK_ERR_INVALID, "world_size must be a power of two and 0 <= rank < world_size");
+    int gbits = 0;
+    while ((1 << gbits) < world_size) ++gbits;
+    if (n_qubits - gbits < 1) return fail(nullptr, XYK_ERR_INVALID, "too few qubits for this world size");
+    if (n_qubits - gbits > 34) return fail(nullptr, XYK_ERR_INVALID, "too many local qubits");
+    std::unique_ptr<xyk_handle_s> h(new xyk_handle_s);
+    h->n = n_qubits;
+    h->gbits = gbits;
+    h->nlocal = n_qubits - gbits;
+    h->world = world_size;
+    h->rank = rank;
+    h->dtype = dtype;
+    h->device = device;
+    h->perm.resize(n_qubits);
+    for (int q = 0; q < n_qubits; ++q) h->perm[q] = q;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, XYK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, XYK_ERR_CUDA, cudaGetErrorString(e));
+    h->sm_count = prop.multiProcessorCount;
+    h->bytes = ((size_t)1 << h->nlocal) * amp_bytes(dtype);
+    e = cudaMalloc(&h->buf[0], h->bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, e == cudaErrorMemoryAllocation ? XYK_ERR_NOMEM : XYK_ERR_CUDA,
+                    std::string("cudaMalloc(state): ") + cudaGetErrorString(e));
+    }
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_tab, sizeof(double2) * 3 * kTabStride) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_partial, sizeof(double) * kPartialDoubles) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_out, sizeof(double) * 4096) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->h_out, sizeof(double) * 4096) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
+    if (!ok) {
+        std::string msg = std::string("scratch allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        xyk_destroy(h.release());
+        return fail(nullptr, XYK_ERR_NOMEM, msg);
+    }
+    *out = h.release();
+    return XYK_OK;
+}
+
+int xyk_destroy(xyk_handle h) {
+    if (!h) return XYK_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int b = 0; b < 2; ++b)
+        if (h->buf[b]) cudaFree(h->buf[b]);
+    if (h->d_tab) cudaFree(h->d_tab);
+    if (h->d_partial) cudaFree(h->d_partial);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return XYK_OK;
+}
+
+int xyk_set_option(xyk_handle h, int option, int64_t value) {
+    if (!h) return XYK_ERR_INVALID;
+    switch (option) {
+        case XYK_OPT_ENGINE:
+            XYK_CHECK(h, value >= 0 && value <= 2, XYK_ERR_INVALID, "unknown engine");
+            h->engine_opt = (int)value;
+            return XYK_OK;
+        case XYK_OPT_FUSE_PHASE:
+            h->fuse_phase = value != 0;
+            return XYK_OK;
+        case XYK_OPT_TILED_OBS:
+            h->tiled_obs = value != 0;
+            return XYK_OK;
+        default:
+            return fail(h, XYK_ERR_INVALID, "unknown option");
+    }
+}
+
+int xyk_set_problem(xyk_handle h, const double* K, const double* omega) {
+    if (!h || !K || !omega) return XYK_ERR_INVALID;
+    for (int i = 0; i < h->n * h->n; ++i) XYK_CHECK(h, std::isfinite(K[i]), XYK_ERR_INVALID, "K must be finite");
+    for (int i = 0; i < h->n; ++i) XYK_CHECK(h, std::isfinite(omega[i]), XYK_ERR_INVALID, "omega must be finite");
+    build_terms(h->n, K, omega, h->pairs, h->zterms, h->Ksym);
+    h->omega.assign(omega, omega + h->n);
+    h->have_problem = true;
+    h->problem_version++;
+    h->programs.clear();
+    return XYK_OK;
+}
+
+int xyk_term_counts(xyk_handle h, int* n_pairs, int* n_z) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->have_problem, XYK_ERR_STATE, "no problem set");
+    if (n_pairs) *n_pairs = (int)h->pairs.size();
+    if (n_z) *n_z = (int)h->zterms.size();
+    return XYK_OK;
+}
+
+int xyk_init_product_state(xyk_handle h) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->have_problem, XYK_ERR_STATE, "no problem set");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    // keep global bits where they are, local qubits in canonical order
+    for (int q = 0; q < h->n; ++q) h->perm[q] = q;
+    int rc = h->dtype == 0 ? launch_init<double>(h) : launch_init<float>(h);
+    if (rc) return rc;
+    h->state_valid = true;
+    return XYK_OK;
+}
+
+int xyk_apply_layers(xyk_handle h, double delta, int order, int reps) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->have_problem, XYK_ERR_STATE, "no problem set");
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CHECK(h, order == 1 || order == 2 || order == 4 || order == 6, XYK_ERR_INVALID, "order must be 1, 2, 4 or 6");
+    XYK_CHECK(h, reps >= 1, XYK_ERR_INVALID, "reps must be >= 1");
+    XYK_CHECK(h, std::isfinite(delta), XYK_ERR_INVALID, "delta must be finite");
+    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "sharded evolution is driven through xyk_continue (not in this build)");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    if (use_tiled(h)) {
+        std::shared_ptr<Program> prog;
+        try {
+            prog = get_program(h, delta, order, reps);
+        } catch (const std::exception& e) {
+            return fail(h, XYK_ERR_INVALID, e.what());
+        }
+        return run_program_tiled(h, *prog);
+    }
+    int l1 = 0;
+    std::vector<Segment> segs = build_sequence(h->pairs, delta, order, reps, &l1);
+    int gates = 0;
+    for (auto& s : segs) gates += (int)s.gates.size();
+    int rc = run_segments_simple(h, segs);
+    h->stats.last_passes = 0;
+    h->stats.last_rounds = 0;
+    h->stats.last_gates = gates;
+    h->stats.last_layers1 = l1;
+    return rc;
+}
+
+int xyk_continue(xyk_handle h) { return fail(h, XYK_ERR_UNSUPPORTED, "not a sharded handle"); }
+int xyk_exchange_info(xyk_handle h, void**, void**, size_t*) { return fail(h, XYK_ERR_UNSUPPORTED, "not a sharded handle"); }
+int xyk_exchange_done(xyk_handle h) { return fail(h, XYK_ERR_UNSUPPORTED, "not a sharded handle"); }
+
+int xyk_xy_expectations(xyk_handle h, double* exp_x, double* exp_y) {
+    if (!h || !exp_x || !exp_y) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    int rc = xy_expect_device(h);
+    if (rc) return rc;
+    XYK_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * 2 * h->n, cudaMemcpyDeviceToHost, h->stream));
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < h->n; ++q) {
+        exp_x[q] = h->h_out[2 * q];
+        exp_y[q] = h->h_out[2 * q + 1];
+    }
+    return XYK_OK;
+}
+
+int xyk_order_parameter(xyk_handle h, double* R, double* psi) {
+    if (!h || !R) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "order parameter of a sharded state is assembled by the host");
+    std::vector<double> ex(h->n), ey(h->n);
+    int rc = xyk_xy_expectations(h, ex.data(), ey.data());
+    if (rc) return rc;
+    double zr = 0.0, zi = 0.0;
+    for (int q = 0; q < h->n; ++q) {
+        zr += ex[q];
+        zi += ey[q];
+    }
+    zr /= h->n;
+    zi /= h->n;
+    *R = std::sqrt(zr * zr + zi * zi);
+    if (psi) *psi = std::atan2(zi, zr);
+    return XYK_OK;
+}
+
+int xyk_z_expectations(xyk_handle h, double* exp_z) {
+    if (!h || !exp_z) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    const uint64_t dim = 1ull << h->nlocal;
+    const int grid = std::min(kRedBlocks, grid_for(h, dim, 256));
+    if (h->dtype == 0)
+        z_expect_kernel<double><<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], h->nlocal, h->d_partial);
+    else
+        z_expect_kernel<float><<<grid, 256, 0, h->stream>>>((const float2*)h->buf[h->cur], h->nlocal, h->d_partial);
+    reduce_partials_kernel<<<kMaxQ + 1, 128, 0, h->stream>>>(h->d_partial, grid, kMaxQ + 1, h->d_out);
+    h->stats.kernel_launches += 2;
+    XYK_CUDA(h, cudaGetLastError());
+    XYK_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (kMaxQ + 1), cudaMemcpyDeviceToHost, h->stream));
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+    const double tot = h->h_out[kMaxQ];
+    for (int q = 0; q < h->n; ++q) {
+        const int pos = h->perm[q];
+        if (pos < h->nlocal) exp_z[q] = tot - 2.0 * h->h_out[pos];
+        else exp_z[q] = ((h->rank >> (pos - h->nlocal)) & 1) ? -tot : tot;
+    }
+    return XYK_OK;
+}
+
+int xyk_norm2(xyk_handle h, double* norm2) {
+    if (!h || !norm2) return XYK_ERR_INVALID;
+    std::vector<double> z(h->n);
+    int rc = xyk_z_expectations(h, z.data());
+    if (rc) return rc;
+    *norm2 = h->h_out[kMaxQ];
+    return XYK_OK;
+}
+
+int xyk_correlation_matrix_xy(xyk_handle h, double* C) {
+    if (!h || !C) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "single-GPU handles only");
+    XYK_CHECK(h, h->n >= 2 || true, XYK_ERR_INVALID, "");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    const int n = h->n;
+    for (int i = 0; i < n * n; ++i) C[i] = 0.0;
+    if (n < 2) return XYK_OK;
+    const uint64_t quarter = 1ull << (h->nlocal - 2);
+    const int grid = std::min(kRedBlocks, grid_for(h, quarter, 256));
+    // batches of pairs: partials for pair index t at d_partial + t*kRedBlocks
+    const int max_batch = kPartialDoubles / kRedBlocks;
+    std::vector<std::pair<int, int>> pairs;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) pairs.push_back({i, j});
+    for (size_t off = 0; off < pairs.size(); off += max_batch) {
+        const int cnt = (int)std::min<size_t>(max_batch, pairs.size() - off);
+        XYK_CHECK(h, cnt <= 4096, XYK_ERR_UNSUPPORTED, "too many pairs per batch");
+        for (int t = 0; t < cnt; ++t) {
+            const int pi = h->perm[pairs[off + t].first], pj = h->perm[pairs[off + t].second];
+            if (h->dtype == 0)
+                xxyy_expect_kernel<double><<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], h->nlocal, pi, pj,
+                                                                      h->d_partial + (size_t)t * kRedBlocks);
+            else
+                xxyy_expect_kernel<float><<<grid, 256, 0, h->stream>>>((const float2*)h->buf[h->cur], h->nlocal, pi, pj,
+                                                                     h->d_partial + (size_t)t * kRedBlocks);
+            h->stats.kernel_launches++;
+        }
+        reduce_rows_kernel<<<cnt, 128, 0, h->stream>>>(h->d_partial, grid, kRedBlocks, h->d_out);
+        h->stats.kernel_launches++;
+        XYK_CUDA(h, cudaGetLastError());
+        XYK_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+        XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (int t = 0; t < cnt; ++t) {
+            const int i = pairs[off + t].first, j = pairs[off + t].second;
+            C[i * n + j] = C[j * n + i] = 4.0 * h->h_out[t];
+        }
+    }
+    return XYK_OK;
+}
+
+int xyk_energy(xyk_handle h, double* E) {
+    if (!h || !E) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->have_problem, XYK_ERR_STATE, "no problem set");
+    const int n = h->n;
+    std::vector<double> C((size_t)n * n), z(n);
+    int rc = xyk_correlation_matrix_xy(h, C.data());
+    if (rc) return rc;
+    rc = xyk_z_expectations(h, z.data());
+    if (rc) return rc;
+    double e = 0.0;
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) e -= h->Ksym[(size_t)i * n + j] * C[(size_t)i * n + j];
+    for (int i = 0; i < n; ++i) e -= h->omega[i] * z[i];
+    *E = e;
+    return XYK_OK;
+}
+
+int xyk_run(xyk_handle h, const double* step_sizes, int m, int reps, int order, double* R_out) {
+    if (!h || !R_out || (m > 0 && !step_sizes)) return XYK_ERR_INVALID;
+    XYK_CHECK(h, m >= 0, XYK_ERR_INVALID, "m must be >= 0");
+    int rc = xyk_init_product_state(h);
+    if (rc) return rc;
+    rc = xyk_order_parameter(h, &R_out[0], nullptr);
+    if (rc) return rc;
+    for (int s = 0; s < m; ++s) {
+        rc = xyk_apply_layers(h, step_sizes[s], order, reps);
+        if (rc) return rc;
+        rc = xyk_order_parameter(h, &R_out[s + 1], nullptr);
+        if (rc) return rc;
+    }
+    return XYK_OK;
+}
+
+int xyk_get_state(xyk_handle h, void* dst, int is_device) {
+    if (!h || !dst) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    const void* src = h->buf[h->cur];
+    if (!perm_is_identity(h)) {
+        // canonical copy into the spare buffer; the live state keeps its layout
+        PermSpec S{};
+        S.nlocal = h->nlocal;
+        for (int b = 0; b < kMaxQ; ++b) S.dst_of_src[b] = (uint8_t)b;
+        for (int q = 0; q < h->n; ++q) {
+            XYK_CHECK(h, (h->perm[q] < h->nlocal) == (q < h->nlocal), XYK_ERR_UNSUPPORTED,
+                      "sharded state must be canonicalised first");
+            if (h->perm[q] < h->nlocal) S.dst_of_src[h->perm[q]] = (uint8_t)q;
+        }
+        int rc = ensure_alt(h);
+        if (rc) return rc;
+        const uint64_t dim = 1ull << h->nlocal;
+        if (h->dtype == 0)
+            permute_kernel<double><<<grid_for(h, dim, 256), 256, 0, h->stream>>>((const double2*)h->buf[h->cur],
+                                                                               (double2*)h->buf[h->cur ^ 1], S);
+        else
+            permute_kernel<float><<<grid_for(h, dim, 256), 256, 0, h->stream>>>((const float2*)h->buf[h->cur],
+                                                                              (float2*)h->buf[h->cur ^ 1], S);
+        h->stats.kernel_launches++;
+        XYK_CUDA(h, cudaGetLastError());
+        src = h->buf[h->cur ^ 1];
+    }
+    XYK_CUDA(h, cudaMemcpyAsync(dst, src, h->bytes, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return XYK_OK;
+}
+
+int xyk_set_state(xyk_handle h, const void* src, int is_device) {
+    if (!h || !src) return XYK_ERR_INVALID;
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    XYK_CUDA(h, cudaMemcpyAsync(h->buf[h->cur], src, h->bytes, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < h->n; ++q) h->perm[q] = q;
+    h->state_valid = true;
+    return XYK_OK;
+}
+
+int xyk_state_buffer(xyk_handle h, void** ptr, size_t* bytes) {
+    if (!h) return XYK_ERR_INVALID;
+    if (ptr) *ptr = h->buf[h->cur];
+    if (bytes) *bytes = h->bytes;
+    return XYK_OK;
+}
+
+int xyk_get_layout(xyk_handle h, int* perm) {
+    if (!h || !perm) return XYK_ERR_INVALID;
+    for (int q = 0; q < h->n; ++q) perm[q] = h->perm[q];
+    return XYK_OK;
+}
+
+int xyk_canonicalise(xyk_handle h) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    std::vector<int> target(h->n);
+    for (int q = 0; q < h->n; ++q) target[q] = q;
+    return relayout(h, target);
+}
+
+int xyk_synchronize(xyk_handle h) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return XYK_OK;
+}
+
+int xyk_stream(xyk_handle h, void** stream) {
+    if (!h || !stream) return XYK_ERR_INVALID;
+    *stream = (void*)h->stream;
+    return XYK_OK;
+}
+
+int xyk_get_stats(xyk_handle h, xyk_stats* out) {
+    if (!h || !out) return XYK_ERR_INVALID;
+    *out = h->stats;
+    return XYK_OK;
+}
+
+int xyk_enable_timing(xyk_handle h, int on) {
+    if (!h) return XYK_ERR_INVALID;
+    h->stats.timing_enabled = on ? 1 : 0;
+    return XYK_OK;
+}
+
+int64_t xyk_plan_describe(int n_local, int dtype, const double* K, const double* omega, int n, double delta,
+                          int order, int reps, char* buf, int64_t cap) {
+    (void)dtype;
+    if (n < 1 || n > kMaxQ || n_local < 1 || n_local > n || !K || !omega) return -1;
+    try {
+        std::vector<PairTerm> pairs;
+        std::vector<ZTerm> z;
+        std::vector<double> Ks;
+        build_terms(n, K, omega, pairs, z, Ks);
+        int l1 = 0;
+        std::vector<Segment> segs = build_sequence(pairs, delta, order, reps, &l1);
+        SchedConfig cfg;
+        cfg.TB = kTB;
+        cfg.RB = kRB;
+        cfg.max_rounds = kMaxRounds;
+        Plan plan = compile_plan(n_local, segs, cfg);
+        plan.layers1_equiv = l1;
+        const std::string js = plan_to_json(plan);
+        if (buf && cap > (int64_t)js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
+        return (int64_t)js.size() + 1;
+    } catch (const std::exception& e) {
+        g_global_error = e.what();
+        return -1;
+    }
+}
+
+int xyk_batch_run(int device, int n, int B, const double* K, const double* omega, const double* step_sizes, int m,
+                  int reps, int order, double* R_out, void* final_states) {
+    return small_batch_run(device, n, B, K, omega, step_sizes, m, reps, order, R_out, final_states, g_global_error);
+}
+
+}  // extern "C"

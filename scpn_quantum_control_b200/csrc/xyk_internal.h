@@ -1,0 +1,93 @@
+// Internal structures shared by the schedule compiler (host C++) and the CUDA engine.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace xyk {
+
+constexpr int kMaxQ = 40;          // maximum number of local qubits handled by one handle
+constexpr double kSparsityEps = 1e-15;  // reference: _constants.py COUPLING_SPARSITY_EPS
+
+struct PairTerm {
+    int i, j;
+    double k;  // symmetrised coupling K_ij
+};
+struct ZTerm {
+    int i;
+    double w;
+};
+
+// One pair rotation of the flattened product-formula sequence.
+struct GateOp {
+    int i, j;    // logical qubits, i < j
+    double phi;  // rotation angle 2 * K_ij * tau_effective
+    int sweep;   // index of the monotone sweep this gate belongs to (a pair occurs once per sweep)
+};
+
+// A diagonal phase of "time" ztau followed by a run of pair gates.
+struct Segment {
+    double ztau;
+    std::vector<GateOp> gates;
+};
+
+// Term list in the reference's order (bridge/knm_hamiltonian.py:172-195).
+void build_terms(int n, const double* K, const double* omega, std::vector<PairTerm>& pairs,
+                 std::vector<ZTerm>& zterms, std::vector<double>& Ksym);
+
+// Flatten `reps` repetitions of the order-`order` formula over one interval `delta`.
+// order 1: LieTrotter; 2: SuzukiTrotter(order=2); 4, 6: Suzuki recursion over the order-2 layer.
+std::vector<Segment> build_sequence(const std::vector<PairTerm>& pairs, double delta, int order,
+                                    int reps, int* layers1_equiv);
+
+struct PlanRound {
+    int regq[8];      // logical qubit of register bit k (ascending for forward sweeps, descending for reverse)
+    int regpos[8];    // tile-local position of register bit k
+    int thrpos[16];   // tile-local position of thread bit b (TB - RB entries)
+    uint32_t mask;    // enabled pair slots, slot order = lexicographic (a, b), a < b over register bits
+    double phi[16];   // angle per slot (only enabled slots are meaningful)
+    int ngates;
+};
+
+struct PlanPass {
+    int tileq[16];                 // logical qubit at tile-local position p (= physical position p on input)
+    std::vector<PlanRound> rounds;
+    int out_of_in[kMaxQ];          // physical input bit b -> physical output bit
+    int n_shared;                  // tile qubits that land on output positions [0, n_shared) (contiguous chunk bits)
+    bool has_phase;                // diagonal phase exp(+i ztau sum w_q (1-2b_q)) applied before the gates
+    double ztau;
+    bool std_rot;                  // some angle too large for the shear (lifting) form
+    int ngates;
+};
+
+struct Plan {
+    int nq = 0;  // local qubits
+    int TB = 0, RB = 0;
+    std::vector<int> start_perm;   // logical -> physical layout the program expects on entry
+    std::vector<int> end_perm;     // layout on exit (== start_perm: programs are cyclic)
+    std::vector<PlanPass> passes;
+    double trailing_ztau = 0.0;    // diagonal phase after the last pass (0 if none)
+    bool has_trailing_phase = false;
+    int total_gates = 0, total_rounds = 0, layers1_equiv = 0;
+};
+
+struct SchedConfig {
+    int TB = 12;           // tile bits (amplitudes per tile = 2^TB)
+    int RB = 5;            // register bits (amplitudes per thread = 2^RB)
+    int need_shared = 3;   // consecutive tiles must share this many qubits (contiguous output chunks)
+    int max_rounds = 14;   // rounds a single pass descriptor can carry
+};
+
+// Compile the segments into tile passes over nq local qubits.  Throws std::runtime_error.
+Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& cfg);
+
+// GF(2)^3 swizzle vector of tile-local position p (positions 0..2 are the identity part).
+inline int swizzle_vec(int p) {
+    static const int V[16] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6, 7, 1, 2};
+    return V[p];
+}
+
+std::string plan_to_json(const Plan& plan);
+
+}  // namespace xyk

@@ -1,0 +1,468 @@
+// CUDA kernels of the Kuramoto-XY statevector engine (sm_100a).
+//
+//  * gate-by-gate kernels (any layout): product-state init, diagonal phase, one pair rotation,
+//    <X_q>/<Y_q>, <Z_q>, <XX+YY>, norm, bit-permuting copy;
+//  * the fused tile pass: one read+write sweep over the state applying every pair rotation
+//    the schedule compiler packed into it, tiles staged in shared memory, 2^RB amplitudes per
+//    thread in registers, output written through a bit permutation.
+//
+// Reference arithmetic being replaced: Qiskit Statevector.evolve of the Trotter circuit
+// (call site src/scpn_quantum_control/phase/xy_kuramoto.py:247) and the Rust observable loops
+// (scpn_quantum_engine/src/pauli.rs:122-214, sectors.rs:105-145).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "xyk_internal.h"
+
+namespace xyk {
+
+template <typename real> struct cplx;
+template <> struct cplx<double> { using type = double2; };
+template <> struct cplx<float> { using type = float2; };
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t swz_mask(int bit, int nbits) {
+    // positions p >= 3 whose swizzle vector has `bit` set
+    uint32_t m = 0;
+    constexpr int V[16] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6, 7, 1, 2};
+    for (int p = 3; p < nbits; ++p)
+        if ((V[p] >> bit) & 1) m |= 1u << p;
+    return m;
+}
+
+// tile-local index -> shared-memory slot: the low three bits (16-byte column inside a 128-byte
+// bank window) are XORed with a GF(2)-linear function of the higher bits, so that any three
+// index bits with independent swizzle vectors spread eight lanes over eight distinct columns.
+template <int TB>
+__device__ __forceinline__ uint32_t swz(uint32_t x) {
+    constexpr uint32_t M0 = swz_mask(0, TB), M1 = swz_mask(1, TB), M2 = swz_mask(2, TB);
+    const uint32_t s = (__popc(x & M0) & 1u) | ((__popc(x & M1) & 1u) << 1) | ((__popc(x & M2) & 1u) << 2);
+    return x ^ s;
+}
+
+__host__ __device__ constexpr int insert_zero(int v, int pos) {
+    return ((v >> pos) << (pos + 1)) | (v & ((1 << pos) - 1));
+}
+
+__device__ __forceinline__ uint64_t insert_zero64(uint64_t v, int pos) {
+    return ((v >> pos) << (pos + 1)) | (v & ((1ull << pos) - 1ull));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of NV values per thread; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* >= NV*32 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) smem[k * 32 + warp] = v[k];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double x = lane < nw ? smem[k * 32 + lane] : 0.0;
+            v[k] = warp_sum(x);
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// gate-by-gate kernels
+// ---------------------------------------------------------------------------------------------
+struct QubitTable {
+    double c[kMaxQ];      // cos(theta_q / 2)
+    double s[kMaxQ];      // sin(theta_q / 2)
+    uint8_t pos[kMaxQ];   // physical bit of logical qubit q; >= nlocal means the bit comes from `rank`
+    int32_t nq;           // total logical qubits
+    int32_t nlocal;       // local physical bits
+    int32_t rank;         // value of the physical bits >= nlocal
+};
+
+// psi0[k] = prod_q (bit_q ? sin : cos)(theta_q/2)     (xy_kuramoto.py:236-242)
+template <typename real>
+__global__ void init_product_kernel(typename cplx<real>::type* __restrict__ psi, const __grid_constant__ QubitTable T) {
+    const uint64_t dim = 1ull << T.nlocal;
+    const uint64_t hi = (uint64_t)T.rank << T.nlocal;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < dim; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t full = p | hi;
+        double v = 1.0;
+        for (int q = 0; q < T.nq; ++q) v *= ((full >> T.pos[q]) & 1ull) ? T.s[q] : T.c[q];
+        typename cplx<real>::type o;
+        o.x = (real)v;
+        o.y = (real)0;
+        psi[p] = o;
+    }
+}
+
+struct PhaseSpec {
+    double w[kMaxQ];     // omega of the logical qubit on physical bit b (0 where dropped), b < nbits
+    int32_t nbits;       // physical bits (local + global)
+    int32_t nlocal;
+    int32_t rank;
+    int32_t b1, b2;      // chunk boundaries: [0,b1) [b1,b2) [b2,nlocal)
+    double tau;
+};
+
+// tables[c][v] = exp(+i tau sum_{b in chunk c} w_b (1 - 2 bit_b(v)))   (A.3 step 1)
+__global__ void phase_table_kernel(double2* __restrict__ tab, const __grid_constant__ PhaseSpec S, int stride) {
+    const int c = blockIdx.y;
+    const int lo = c == 0 ? 0 : (c == 1 ? S.b1 : S.b2);
+    const int hi = c == 0 ? S.b1 : (c == 1 ? S.b2 : S.nlocal);
+    const int cnt = 1 << (hi - lo);
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < cnt; v += gridDim.x * blockDim.x) {
+        double ph = 0.0;
+        for (int b = lo; b < hi; ++b) ph += S.w[b] * (1.0 - 2.0 * (double)((v >> (b - lo)) & 1));
+        if (c == 2)  // global bits (fixed by the rank) ride on the last chunk
+            for (int b = S.nlocal; b < S.nbits; ++b)
+                ph += S.w[b] * (1.0 - 2.0 * (double)((S.rank >> (b - S.nlocal)) & 1));
+        double sn, cs;
+        sincos(S.tau * ph, &sn, &cs);
+        tab[(size_t)c * stride + v] = make_double2(cs, sn);
+    }
+}
+
+template <typename real>
+__global__ void phase_apply_kernel(typename cplx<real>::type* __restrict__ psi, const double2* __restrict__ tab,
+                                   int stride, int nlocal, int b1, int b2) {
+    const uint64_t dim = 1ull << nlocal;
+    const uint32_t m0 = (1u << b1) - 1u, m1 = (1u << (b2 - b1)) - 1u;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < dim; p += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 t0 = __ldg(&tab[(uint32_t)p & m0]);
+        const double2 t1 = __ldg(&tab[stride + ((uint32_t)(p >> b1) & m1)]);
+        const double2 t2 = __ldg(&tab[2 * stride + (uint32_t)(p >> b2)]);
+        const double ar = t0.x * t1.x - t0.y * t1.y, ai = t0.x * t1.y + t0.y * t1.x;
+        const double fr = ar * t2.x - ai * t2.y, fi = ar * t2.y + ai * t2.x;
+        typename cplx<real>::type v = psi[p];
+        const double xr = (double)v.x, xi = (double)v.y;
+        v.x = (real)(xr * fr - xi * fi);
+        v.y = (real)(xr * fi + xi * fr);
+        psi[p] = v;
+    }
+}
+
+// (a, b) = (psi[..1_pi..0_pj..], psi[..0_pi..1_pj..]) <- (c a + i s b, c b + i s a)   (A.3 step 2)
+template <typename real>
+__global__ void pair_gate_kernel(typename cplx<real>::type* __restrict__ psi, int nlocal, int pi, int pj, double c,
+                                 double s) {
+    const uint64_t quarter = 1ull << (nlocal - 2);
+    const int lo = pi < pj ? pi : pj, hi = pi < pj ? pj : pi;
+    const uint64_t mi = 1ull << pi, mj = 1ull << pj;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < quarter; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = insert_zero64(insert_zero64(t, lo), hi);
+        typename cplx<real>::type a = psi[k | mi], b = psi[k | mj];
+        const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+        a.x = (real)(c * ar - s * bi);
+        a.y = (real)(c * ai + s * br);
+        b.x = (real)(c * br - s * ai);
+        b.y = (real)(c * bi + s * ar);
+        psi[k | mi] = a;
+        psi[k | mj] = b;
+    }
+}
+
+// partial[blockIdx.x] = (sum_k Re conj(psi_k) psi_{k|m}, sum_k Im ...) over k with bit `pos` clear
+// (scpn_quantum_engine/src/pauli.rs:195-211, without the factor 2)
+template <typename real>
+__global__ void xy_expect_kernel(const typename cplx<real>::type* __restrict__ psi, int nlocal, int pos,
+                                 double2* __restrict__ partial) {
+    __shared__ double red[2 * 32];
+    const uint64_t half = 1ull << (nlocal - 1);
+    const uint64_t m = 1ull << pos;
+    double acc[2] = {0.0, 0.0};
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < half; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = insert_zero64(t, pos);
+        const typename cplx<real>::type a = psi[k], b = psi[k | m];
+        acc[0] += (double)a.x * (double)b.x + (double)a.y * (double)b.y;
+        acc[1] += (double)a.x * (double)b.y - (double)a.y * (double)b.x;
+    }
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(acc[0], acc[1]);
+}
+
+// partial[blockIdx.x][b] = sum_k (1 - 2 bit_b(k)) |psi_k|^2 for every physical bit b < nlocal,
+// partial[blockIdx.x][nlocal] = sum_k |psi_k|^2     (pauli.rs:163-170)
+template <typename real>
+__global__ void z_expect_kernel(const typename cplx<real>::type* __restrict__ psi, int nlocal,
+                                double* __restrict__ partial /* [grid][kMaxQ+1] */) {
+    __shared__ double red[32];
+    const uint64_t dim = 1ull << nlocal;
+    // per-thread: total weight and weight with bit b set, for b < nlocal (registers: dynamic loop
+    // kept rolled over b with a small local array)
+    double w1[kMaxQ];
+#pragma unroll
+    for (int b = 0; b < kMaxQ; ++b) w1[b] = 0.0;
+    double tot = 0.0;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < dim; p += (uint64_t)gridDim.x * blockDim.x) {
+        const typename cplx<real>::type a = psi[p];
+        const double pr = (double)a.x * (double)a.x + (double)a.y * (double)a.y;
+        tot += pr;
+#pragma unroll
+        for (int b = 0; b < kMaxQ; ++b) w1[b] += ((p >> b) & 1ull) ? pr : 0.0;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int b = 0; b <= kMaxQ; ++b) {
+        double v = b < kMaxQ ? w1[b < kMaxQ ? b : 0] : tot;
+        v = warp_sum(v);
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            double x = lane < nw ? red[lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0) partial[(size_t)blockIdx.x * (kMaxQ + 1) + b] = x;
+        }
+        __syncthreads();
+    }
+}
+
+// partial[blockIdx.x] = sum over k with bit pi = 1, bit pj = 0 of Re conj(psi_k) psi_{k ^ (mi|mj)}
+// (sectors.rs:105-145: C_ij = 4 * that sum)
+template <typename real>
+__global__ void xxyy_expect_kernel(const typename cplx<real>::type* __restrict__ psi, int nlocal, int pi, int pj,
+                                   double* __restrict__ partial) {
+    __shared__ double red[32];
+    const uint64_t quarter = 1ull << (nlocal - 2);
+    const int lo = pi < pj ? pi : pj, hi = pi < pj ? pj : pi;
+    const uint64_t mi = 1ull << pi, mj = 1ull << pj;
+    double acc[1] = {0.0};
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < quarter; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = insert_zero64(insert_zero64(t, lo), hi);
+        const typename cplx<real>::type a = psi[k | mi], b = psi[k | mj];
+        acc[0] += (double)a.x * (double)b.x + (double)a.y * (double)b.y;
+    }
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc[0];
+}
+
+// out[j] = sum_b partial[b * stride + j]   (deterministic second reduction stage; one block per j)
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nblocks, int stride,
+                                       double* __restrict__ out) {
+    __shared__ double red[32];
+    const int j = blockIdx.x;
+    double acc[1] = {0.0};
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc[0] += partial[(size_t)b * stride + j];
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) out[j] = acc[0];
+}
+
+// out[t] = sum_b partial[t * stride + b]   (row layout; one block per t)
+__global__ void reduce_rows_kernel(const double* __restrict__ partial, int nblocks, int stride,
+                                   double* __restrict__ out) {
+    __shared__ double red[32];
+    const int t = blockIdx.x;
+    double acc[1] = {0.0};
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc[0] += partial[(size_t)t * stride + b];
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) out[t] = acc[0];
+}
+
+// out[2q] = <X_q> = 2 sum_b partial[q*stride+b].x, out[2q+1] = <Y_q>   (one block per qubit)
+__global__ void xy_finalize_kernel(const double2* __restrict__ partial, int nblocks, int stride,
+                                   double* __restrict__ out) {
+    __shared__ double red[2 * 32];
+    const int q = blockIdx.x;
+    double acc[2] = {0.0, 0.0};
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+        const double2 v = partial[(size_t)q * stride + b];
+        acc[0] += v.x;
+        acc[1] += v.y;
+    }
+    block_sum<2>(acc, red);
+    if (threadIdx.x == 0) {
+        out[2 * q] = 2.0 * acc[0];
+        out[2 * q + 1] = 2.0 * acc[1];
+    }
+}
+
+struct PermSpec {
+    uint8_t dst_of_src[kMaxQ];  // source physical bit b -> destination physical bit
+    int32_t nlocal;
+};
+
+// dst[perm(p)] = src[p].  Gather form: the thread index runs over the DESTINATION so that
+// writes are coalesced.
+template <typename real>
+__global__ void permute_kernel(const typename cplx<real>::type* __restrict__ src,
+                               typename cplx<real>::type* __restrict__ dst, const __grid_constant__ PermSpec S) {
+    const uint64_t dim = 1ull << S.nlocal;
+    for (uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; d < dim; d += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = 0;
+        for (int b = 0; b < S.nlocal; ++b) s |= ((d >> S.dst_of_src[b]) & 1ull) << b;
+        dst[d] = src[s];
+    }
+}
+
+template <typename from, typename to>
+__global__ void convert_kernel(const typename cplx<from>::type* __restrict__ src,
+                               typename cplx<to>::type* __restrict__ dst, uint64_t count) {
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < count; p += (uint64_t)gridDim.x * blockDim.x) {
+        typename cplx<to>::type o;
+        o.x = (to)src[p].x;
+        o.y = (to)src[p].y;
+        dst[p] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused tile pass
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxRounds = 14;
+
+template <int TB, int RB>
+struct PassDesc {
+    static constexpr int NT = TB - RB;
+    static constexpr int NSLOT = RB * (RB - 1) / 2;
+    struct Round {
+        uint8_t thrpos[8];  // tile-local position of thread bit b (NT used)
+        uint8_t regpos[8];  // tile-local position of register bit k (RB used)
+        uint32_t mask;      // enabled pair slots
+        uint32_t pad;
+        double ca[NSLOT];   // shear form: -tan(phi/2); standard form: cos(phi)
+        double cb[NSLOT];   // sin(phi)
+    };
+    int32_t nq;             // local qubits
+    int32_t nrounds;
+    int32_t has_phase;
+    int32_t pad0;
+    uint8_t hi_out[kMaxQ];  // output bit of input bit TB + b (the tile-id bits)
+    uint8_t st_lsrc[16];    // tile-local position of the tile bit with the m-th smallest output bit
+    uint8_t st_odst[16];    // that output bit
+    Round rounds[kMaxRounds];
+};
+
+template <bool LIFT>
+__device__ __forceinline__ void rotate2(double& x, double& y, double ca, double cb) {
+    if constexpr (LIFT) {  // three shears: R(phi) = Sx(-tan(phi/2)) Sy(sin phi) Sx(-tan(phi/2))
+        x = fma(ca, y, x);
+        y = fma(cb, x, y);
+        x = fma(ca, y, x);
+    } else {
+        const double nx = fma(ca, x, -cb * y);
+        const double ny = fma(cb, x, ca * y);
+        x = nx;
+        y = ny;
+    }
+}
+
+template <int TB, int RB, bool LIFT, int MINB>
+__global__ void __launch_bounds__(1 << (TB - RB), MINB)
+tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
+                 const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles) {
+    constexpr int NT = TB - RB, NREG = 1 << RB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* tile = reinterpret_cast<double2*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+
+    // per-thread constants of the load and store phases
+    const uint32_t ld_slot = swz<TB>(tid);  // index bits [0, NT) <- thread id
+    uint32_t st_l = 0;
+    uint64_t st_d = 0;
+#pragma unroll
+    for (int b = 0; b < NT; ++b)
+        if ((tid >> b) & 1u) {
+            st_l |= 1u << P.st_lsrc[b];
+            st_d |= 1ull << P.st_odst[b];
+        }
+    st_l = swz<TB>(st_l);
+
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // ---- load: the tile is one contiguous run of 2^TB amplitudes ----
+        const double2* src = in + (t << TB);
+#pragma unroll
+        for (int k = 0; k < NREG; ++k) {
+            const uint32_t hi = swz<TB>((uint32_t)k << NT);  // compile-time constant after unrolling
+            cp_async16(&tile[ld_slot ^ hi], src + ((uint32_t)k << NT) + tid);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+
+        // ---- register rounds ----
+        for (int r = 0; r < P.nrounds; ++r) {
+            const typename PassDesc<TB, RB>::Round& R = P.rounds[r];
+            uint32_t base = 0;
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+                if ((tid >> b) & 1u) base |= 1u << R.thrpos[b];
+            base = swz<TB>(base);
+            uint32_t rb[RB];
+#pragma unroll
+            for (int k = 0; k < RB; ++k) rb[k] = swz<TB>(1u << R.regpos[k]);
+            double2 a[NREG];
+#pragma unroll
+            for (int j = 0; j < NREG; ++j) {
+                uint32_t off = 0;
+#pragma unroll
+                for (int k = 0; k < RB; ++k)
+                    if ((j >> k) & 1) off ^= rb[k];
+                a[j] = tile[base ^ off];
+            }
+            const uint32_t mask = R.mask;
+#pragma unroll
+            for (int x = 0; x < RB; ++x) {
+#pragma unroll
+                for (int y = x + 1; y < RB; ++y) {
+                    const int slot = x * RB - x * (x + 1) / 2 + (y - x - 1);
+                    if (mask & (1u << slot)) {
+                        const double ca = R.ca[slot], cb = R.cb[slot];
+#pragma unroll
+                        for (int m = 0; m < NREG / 4; ++m) {
+                            const int j0 = insert_zero(insert_zero(m, x), y);
+                            const int jA = j0 | (1 << x), jB = j0 | (1 << y);
+                            rotate2<LIFT>(a[jA].x, a[jB].y, ca, cb);
+                            rotate2<LIFT>(a[jB].x, a[jA].y, ca, cb);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NREG; ++j) {
+                uint32_t off = 0;
+#pragma unroll
+                for (int k = 0; k < RB; ++k)
+                    if ((j >> k) & 1) off ^= rb[k];
+                tile[base ^ off] = a[j];
+            }
+            __syncthreads();
+        }
+
+        // ---- store through the bit permutation ----
+        uint64_t obase = 0;
+        for (int b = 0; b < P.nq - TB; ++b)
+            if ((t >> b) & 1ull) obase |= 1ull << P.hi_out[b];
+        double2* dst = out + obase + st_d;
+#pragma unroll
+        for (int k = 0; k < NREG; ++k) {
+            uint32_t lk = 0;
+            uint64_t dk = 0;
+#pragma unroll
+            for (int b = 0; b < RB; ++b)
+                if ((k >> b) & 1) {
+                    lk |= 1u << P.st_lsrc[NT + b];
+                    dk |= 1ull << P.st_odst[NT + b];
+                }
+            dst[dk] = tile[st_l ^ swz<TB>(lk)];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace xyk

@@ -1,0 +1,544 @@
+// Schedule compiler: turns the reference's ordered gate list into cache-blocked tile passes.
+//
+// The reference applies, per Trotter layer, one diagonal phase and then every pair rotation
+// exp(-i theta_ij (X_iX_j + Y_iY_j)) in lexicographic (i, j) order
+// (reference: src/scpn_quantum_control/bridge/knm_hamiltonian.py:176-195 gives the term order,
+// Qiskit's LieTrotter / SuzukiTrotter apply the terms in list order).  Two rotations commute
+// iff they share no qubit, so any execution order that preserves the relative order of every
+// pair of gates sharing a qubit is the same operator.  The compiler groups gates into
+//   pass  = one read+write sweep over the state; 2^TB-amplitude tiles live in shared memory;
+//   round = one shared-memory round trip; each thread holds 2^RB amplitudes in registers and
+//           applies every enabled rotation among its RB register qubits;
+// and chooses, for every pass, the bit permutation its store applies so that the next pass
+// finds its tile qubits on the lowest physical index bits (contiguous tiles).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+#include <stdexcept>
+
+#include "xyk_internal.h"
+
+namespace xyk {
+
+void build_terms(int n, const double* K, const double* omega, std::vector<PairTerm>& pairs,
+                 std::vector<ZTerm>& zterms, std::vector<double>& Ksym) {
+    pairs.clear();
+    zterms.clear();
+    Ksym.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+            if (i != j) Ksym[(size_t)i * n + j] = (K[(size_t)i * n + j] + K[(size_t)j * n + i]) / 2.0;
+    for (int i = 0; i < n; ++i)
+        if (std::fabs(omega[i]) > kSparsityEps) zterms.push_back({i, omega[i]});
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            const double k = Ksym[(size_t)i * n + j];
+            if (std::fabs(k) < kSparsityEps) continue;
+            pairs.push_back({i, j, k});
+        }
+}
+
+static void suzuki_fracs(int order, std::vector<double>& out) {
+    if (order == 2) {
+        out.push_back(1.0);
+        return;
+    }
+    const double p = 1.0 / (4.0 - std::pow(4.0, 1.0 / (order - 1)));
+    std::vector<double> inner;
+    suzuki_fracs(order - 2, inner);
+    const double w[5] = {p, p, 1.0 - 4.0 * p, p, p};
+    for (double ww : w)
+        for (double f : inner) out.push_back(ww * f);
+}
+
+std::vector<Segment> build_sequence(const std::vector<PairTerm>& pairs, double delta, int order,
+                                    int reps, int* layers1_equiv) {
+    std::vector<Segment> segs;
+    const double tau = delta / reps;
+    const int M = (int)pairs.size();
+    int sweep = 0;
+    if (order == 1) {
+        for (int r = 0; r < reps; ++r) {
+            Segment s;
+            s.ztau = tau;
+            for (const auto& p : pairs) s.gates.push_back({p.i, p.j, 2.0 * p.k * tau, sweep});
+            ++sweep;
+            segs.push_back(std::move(s));
+        }
+        if (layers1_equiv) *layers1_equiv = reps;
+        return segs;
+    }
+    std::vector<double> fr;
+    suzuki_fracs(order, fr);
+    double pending_z = 0.0;
+    for (int r = 0; r < reps; ++r)
+        for (double f : fr) {
+            const double t = f * tau;
+            Segment s;
+            if (M == 0) {  // diagonal only: the two half phases merge
+                pending_z += t;
+                continue;
+            }
+            s.ztau = pending_z + t / 2.0;
+            for (int k = 0; k < M - 1; ++k)
+                s.gates.push_back({pairs[k].i, pairs[k].j, 2.0 * pairs[k].k * t / 2.0, sweep});
+            s.gates.push_back({pairs[M - 1].i, pairs[M - 1].j, 2.0 * pairs[M - 1].k * t, sweep});
+            ++sweep;
+            for (int k = M - 2; k >= 0; --k)
+                s.gates.push_back({pairs[k].i, pairs[k].j, 2.0 * pairs[k].k * t / 2.0, sweep});
+            ++sweep;
+            pending_z = t / 2.0;
+            segs.push_back(std::move(s));
+        }
+    if (pending_z != 0.0 || segs.empty()) {
+        Segment s;
+        s.ztau = pending_z;
+        segs.push_back(std::move(s));
+    }
+    if (layers1_equiv) *layers1_equiv = 2 * reps * (int)fr.size();
+    return segs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dependency-closed executable set
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Gate {
+    int i, j, sweep;
+    bool reverse;  // gate belongs to a descending sweep
+};
+
+// Gates of `g` (not yet done, index >= start) executable when only the qubits of `tmask` are
+// on chip: scanning in sequence order, a gate runs iff both qubits are on chip and neither
+// has been blocked by an earlier gate that could not run.
+void closure(const std::vector<Gate>& g, const std::vector<char>& done, int start, uint64_t tmask,
+             std::vector<int>& out) {
+    out.clear();
+    uint64_t blocked = 0;
+    for (int idx = start; idx < (int)g.size(); ++idx) {
+        if (done[idx]) continue;
+        const uint64_t m = (1ull << g[idx].i) | (1ull << g[idx].j);
+        if ((m & tmask) == m && !(m & blocked)) out.push_back(idx);
+        else blocked |= m;
+        if (__builtin_popcountll(tmask & ~blocked) < 2) break;
+    }
+}
+
+// Same, restricted to what ONE register round can do: a single sweep (monotone order) and each
+// pair at most once.
+void round_closure(const std::vector<Gate>& g, const std::vector<int>& cand, const std::vector<char>& cdone,
+                   uint64_t rmask, std::vector<int>& out) {
+    out.clear();
+    uint64_t blocked = 0;
+    int sweep = -1;
+    for (int c = 0; c < (int)cand.size(); ++c) {
+        if (cdone[c]) continue;
+        const Gate& q = g[cand[c]];
+        const uint64_t m = (1ull << q.i) | (1ull << q.j);
+        const bool fits = (m & rmask) == m && !(m & blocked) && (sweep < 0 || q.sweep == sweep);
+        if (fits) {
+            out.push_back(c);
+            sweep = q.sweep;
+        } else {
+            blocked |= m;
+        }
+        if (__builtin_popcountll(rmask & ~blocked) < 2) break;
+    }
+}
+
+int popc(uint64_t x) { return __builtin_popcountll(x); }
+
+}  // namespace
+
+Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& cfg) {
+    if (nq < 1 || nq > kMaxQ) throw std::runtime_error("compile_plan: bad qubit count");
+    const int TB = std::min(cfg.TB, nq);
+    const int RB = std::min(cfg.RB, TB);
+    Plan plan;
+    plan.nq = nq;
+    plan.TB = TB;
+    plan.RB = RB;
+
+    // ---- 1. choose the tile (set of TB logical qubits) of every pass, segment by segment ----
+    struct RawPass {
+        uint64_t tmask;
+        int seg;
+        std::vector<int> gate_idx;  // indices into the segment's gate list
+        bool has_phase;
+    };
+    std::vector<RawPass> raw;
+    std::vector<std::vector<Gate>> sg(segs.size());
+    for (size_t s = 0; s < segs.size(); ++s) {
+        int last_sweep = -1, sweep_no = -1;
+        for (size_t k = 0; k < segs[s].gates.size(); ++k) {
+            const GateOp& go = segs[s].gates[k];
+            if (go.i < 0 || go.j >= nq || go.i >= go.j) throw std::runtime_error("compile_plan: bad gate");
+            if (go.sweep != last_sweep) {
+                last_sweep = go.sweep;
+                ++sweep_no;
+            }
+            // a sweep is descending iff its first two gates are in descending lexicographic order;
+            // decided below once the whole sweep is known
+            sg[s].push_back({go.i, go.j, go.sweep, false});
+        }
+        // direction per sweep
+        size_t a = 0;
+        while (a < sg[s].size()) {
+            size_t b = a;
+            while (b < sg[s].size() && sg[s][b].sweep == sg[s][a].sweep) ++b;
+            bool rev = false;
+            if (b - a >= 2) {
+                const Gate &x = sg[s][a], &y = sg[s][a + 1];
+                rev = (x.i > y.i) || (x.i == y.i && x.j > y.j);
+            }
+            for (size_t k = a; k < b; ++k) sg[s][k].reverse = rev;
+            a = b;
+        }
+    }
+
+    // diagonal phases of gate-free segments commute with everything diagonal: merge them forward
+    std::vector<double> zeff(segs.size(), 0.0);
+    {
+        double carry = 0.0;
+        for (size_t s = 0; s < segs.size(); ++s) {
+            if (segs[s].gates.empty()) carry += segs[s].ztau;
+            else {
+                zeff[s] = segs[s].ztau + carry;
+                carry = 0.0;
+            }
+        }
+        plan.trailing_ztau = carry;
+        plan.has_trailing_phase = carry != 0.0;
+    }
+
+    const uint64_t all_mask = nq >= 64 ? ~0ull : ((1ull << nq) - 1);
+    auto grow_tile = [&](const std::vector<Gate>& g, const std::vector<char>& done, int first,
+                         uint64_t prev, uint64_t firstTile, int need_prev, int need_first) -> uint64_t {
+        uint64_t T = (1ull << g[first].i) | (1ull << g[first].j);
+        std::vector<int> ex;
+        while (popc(T) < TB) {
+            const int slots = TB - popc(T);
+            const int def_prev = prev ? std::max(0, need_prev - popc(T & prev)) : 0;
+            const int def_first = firstTile ? std::max(0, need_first - popc(T & firstTile)) : 0;
+            uint64_t cands = all_mask & ~T;
+            // when the remaining slots are just enough, only qubits that reduce a deficit qualify
+            if (def_prev + def_first >= slots) {
+                uint64_t c2 = 0;
+                if (def_prev) c2 |= prev & ~T;
+                if (def_first) c2 |= firstTile & ~T;
+                // prefer qubits that reduce both deficits when both are outstanding
+                if (def_prev && def_first && (prev & firstTile & ~T)) c2 = prev & firstTile & ~T;
+                if (c2) cands = c2;
+            }
+            int best = -1, bq = -1, bshare = -1;
+            for (int q = 0; q < nq; ++q) {
+                if (!((cands >> q) & 1)) continue;
+                closure(g, done, first, T | (1ull << q), ex);
+                const int sc = (int)ex.size();
+                const int share = (int)((prev >> q) & 1);
+                if (sc > best || (sc == best && share > bshare)) {
+                    best = sc;
+                    bq = q;
+                    bshare = share;
+                }
+            }
+            if (bq < 0) break;
+            T |= 1ull << bq;
+        }
+        return T;
+    };
+
+    uint64_t prev_tile = 0, first_tile = 0;
+    const int need = std::min(cfg.need_shared, TB);
+    for (size_t s = 0; s < segs.size(); ++s) {
+        const std::vector<Gate>& g = sg[s];
+        if (g.empty()) continue;
+        std::vector<char> done(g.size(), 0);
+        size_t ndone = 0;
+        bool first_of_seg = true;
+        int first = 0;
+        while (ndone < g.size()) {
+            while (done[first]) ++first;
+            uint64_t T = grow_tile(g, done, first, prev_tile, 0, need, 0);
+            RawPass rp;
+            rp.tmask = T;
+            rp.seg = (int)s;
+            rp.has_phase = first_of_seg;
+            closure(g, done, first, T, rp.gate_idx);
+            if (rp.gate_idx.empty()) throw std::runtime_error("compile_plan: no progress");
+            for (int k : rp.gate_idx) done[k] = 1;
+            ndone += rp.gate_idx.size();
+            first_of_seg = false;
+            if (!first_tile) first_tile = T;
+            prev_tile = T;
+            raw.push_back(std::move(rp));
+        }
+    }
+    // cyclic closure: the last tile must share `need` qubits with the first one so that the
+    // program can be replayed from its own end layout.  If it does not, peel gates off the last
+    // pass(es) and re-plan them with the extra constraint.
+    if (!raw.empty() && popc(raw.back().tmask & first_tile) < need && nq > TB) {
+        const int s = raw.back().seg;
+        const std::vector<Gate>& g = sg[s];
+        // undo the last pass of segment s and re-plan the remaining gates of s
+        std::vector<char> done(g.size(), 1);
+        const bool had_phase = raw.back().has_phase;
+        for (int k : raw.back().gate_idx) done[k] = 0;
+        raw.pop_back();
+        prev_tile = raw.empty() ? 0 : raw.back().tmask;
+        size_t ndone = 0;
+        for (char d : done) ndone += d;
+        bool first_of_seg = had_phase;
+        int first = 0;
+        while (ndone < g.size()) {
+            while (done[first]) ++first;
+            uint64_t T = grow_tile(g, done, first, prev_tile, first_tile, need, need);
+            RawPass rp;
+            rp.tmask = T;
+            rp.seg = s;
+            rp.has_phase = first_of_seg;
+            closure(g, done, first, T, rp.gate_idx);
+            if (rp.gate_idx.empty()) throw std::runtime_error("compile_plan: no progress (cyclic)");
+            for (int k : rp.gate_idx) done[k] = 1;
+            ndone += rp.gate_idx.size();
+            first_of_seg = false;
+            prev_tile = T;
+            raw.push_back(std::move(rp));
+        }
+        if (raw.empty()) first_tile = 0;
+    }
+
+    // ---- 2. layouts: tile qubits of pass p sit on physical bits [0, TB) before pass p ----
+    // layout_of(p): shared qubits with the previous tile first (ascending), then the other tile
+    // qubits ascending, then every other qubit ascending.
+    const int P = (int)raw.size();
+    auto make_layout = [&](uint64_t tile, uint64_t prev, std::vector<int>& perm, int& nshared) {
+        perm.assign(nq, -1);
+        int pos = 0;
+        const uint64_t shared = tile & prev;
+        nshared = popc(shared);
+        for (int q = 0; q < nq; ++q)
+            if ((shared >> q) & 1) perm[q] = pos++;
+        for (int q = 0; q < nq; ++q)
+            if (((tile & ~shared) >> q) & 1) perm[q] = pos++;
+        for (int q = 0; q < nq; ++q)
+            if (!((tile >> q) & 1)) perm[q] = pos++;
+    };
+    std::vector<std::vector<int>> layouts(P + 1);
+    std::vector<int> nshared(P + 1, 0);
+    for (int p = 0; p < P; ++p) {
+        const uint64_t prev = p == 0 ? raw[P - 1].tmask : raw[p - 1].tmask;
+        make_layout(raw[p].tmask, P == 1 ? 0 : prev, layouts[p], nshared[p]);
+    }
+    if (P > 0) {
+        layouts[P] = layouts[0];
+        nshared[P] = nshared[0];
+        plan.start_perm = layouts[0];
+        plan.end_perm = layouts[0];
+    } else {
+        plan.start_perm.resize(nq);
+        for (int q = 0; q < nq; ++q) plan.start_perm[q] = q;
+        plan.end_perm = plan.start_perm;
+    }
+
+    // ---- 3. rounds of every pass ----
+    std::vector<int> subset(RB);
+    for (int p = 0; p < P; ++p) {
+        const RawPass& rp = raw[p];
+        const std::vector<Gate>& g = sg[rp.seg];
+        const std::vector<GateOp>& gop = segs[rp.seg].gates;
+        PlanPass pp;
+        std::memset(pp.tileq, -1, sizeof(pp.tileq));
+        const std::vector<int>& lay = layouts[p];
+        int qpos[64];
+        for (int q = 0; q < nq; ++q) {
+            qpos[q] = lay[q];
+            if (lay[q] < TB) pp.tileq[lay[q]] = q;
+        }
+        for (int b = 0; b < kMaxQ; ++b) pp.out_of_in[b] = b;
+        {
+            std::vector<int> inv(nq);
+            for (int q = 0; q < nq; ++q) inv[lay[q]] = q;
+            for (int b = 0; b < nq; ++b) pp.out_of_in[b] = layouts[p + 1][inv[b]];
+        }
+        pp.n_shared = nshared[p + 1];
+        if (P == 1) pp.n_shared = TB;
+        pp.has_phase = rp.has_phase && zeff[rp.seg] != 0.0;
+        pp.ztau = pp.has_phase ? zeff[rp.seg] : 0.0;
+        pp.std_rot = false;
+        pp.ngates = (int)rp.gate_idx.size();
+
+        std::vector<char> cdone(rp.gate_idx.size(), 0);
+        size_t ndone = 0;
+        std::vector<int> ex, bestex;
+        std::vector<int> tq;  // tile qubits
+        for (int q = 0; q < nq; ++q)
+            if ((rp.tmask >> q) & 1) tq.push_back(q);
+        const int tn = (int)tq.size();
+        while (ndone < rp.gate_idx.size()) {
+            // exhaustive search over RB-subsets of the tile qubits
+            uint64_t bestmask = 0;
+            bestex.clear();
+            std::vector<int> idx(RB);
+            for (int k = 0; k < RB; ++k) idx[k] = k;
+            while (true) {
+                uint64_t rm = 0;
+                for (int k = 0; k < RB; ++k) rm |= 1ull << tq[idx[k]];
+                round_closure(g, rp.gate_idx, cdone, rm, ex);
+                if (ex.size() > bestex.size()) {
+                    bestex = ex;
+                    bestmask = rm;
+                }
+                int k = RB - 1;
+                while (k >= 0 && idx[k] == tn - RB + k) --k;
+                if (k < 0) break;
+                ++idx[k];
+                for (int m = k + 1; m < RB; ++m) idx[m] = idx[m - 1] + 1;
+            }
+            if (bestex.empty()) throw std::runtime_error("compile_plan: round search made no progress");
+            PlanRound pr;
+            std::memset(&pr, 0, sizeof(pr));
+            const bool rev = g[rp.gate_idx[bestex[0]]].reverse;
+            std::vector<int> rq;
+            for (int q = 0; q < nq; ++q)
+                if ((bestmask >> q) & 1) rq.push_back(q);
+            if (rev) std::reverse(rq.begin(), rq.end());
+            for (int k = 0; k < RB; ++k) {
+                pr.regq[k] = rq[k];
+                pr.regpos[k] = qpos[rq[k]];
+            }
+            // thread bits: three positions with linearly independent swizzle vectors first
+            std::vector<int> freepos;
+            for (int pos = 0; pos < TB; ++pos) {
+                bool isreg = false;
+                for (int k = 0; k < RB; ++k) isreg |= (pr.regpos[k] == pos);
+                if (!isreg) freepos.push_back(pos);
+            }
+            const int nthr = (int)freepos.size();
+            std::vector<int> order;
+            {
+                int pick[3] = {-1, -1, -1};
+                bool found = false;
+                for (int a = 0; a < nthr && !found; ++a)
+                    for (int b = a + 1; b < nthr && !found; ++b)
+                        for (int c = b + 1; c < nthr && !found; ++c) {
+                            const int va = swizzle_vec(freepos[a]), vb = swizzle_vec(freepos[b]),
+                                      vc = swizzle_vec(freepos[c]);
+                            if (va != vb && va != vc && vb != vc && (va ^ vb) != vc) {
+                                pick[0] = a; pick[1] = b; pick[2] = c;
+                                found = true;
+                            }
+                        }
+                std::vector<char> used(nthr, 0);
+                if (found)
+                    for (int k = 0; k < 3; ++k) {
+                        order.push_back(freepos[pick[k]]);
+                        used[pick[k]] = 1;
+                    }
+                for (int a = 0; a < nthr; ++a)
+                    if (!used[a]) order.push_back(freepos[a]);
+            }
+            for (int b = 0; b < nthr; ++b) pr.thrpos[b] = order[b];
+            // slots
+            for (int c : bestex) {
+                const Gate& q = g[rp.gate_idx[c]];
+                int a = -1, b = -1;
+                for (int k = 0; k < RB; ++k) {
+                    if (pr.regq[k] == q.i || pr.regq[k] == q.j) {
+                        if (a < 0) a = k;
+                        else b = k;
+                    }
+                }
+                // slot index of (a, b), a < b, lexicographic
+                int slot = 0;
+                for (int x = 0; x < a; ++x) slot += RB - 1 - x;
+                slot += b - a - 1;
+                pr.mask |= 1u << slot;
+                pr.phi[slot] = gop[rp.gate_idx[c]].phi;
+                cdone[c] = 1;
+            }
+            pr.ngates = (int)bestex.size();
+            ndone += bestex.size();
+            pp.rounds.push_back(pr);
+        }
+        plan.total_gates += pp.ngates;
+        plan.total_rounds += (int)pp.rounds.size();
+        plan.passes.push_back(std::move(pp));
+    }
+    // split passes that carry more rounds than one descriptor can hold
+    {
+        std::vector<PlanPass> out;
+        for (auto& pp : plan.passes) {
+            if ((int)pp.rounds.size() <= cfg.max_rounds) {
+                out.push_back(std::move(pp));
+                continue;
+            }
+            // identity-layout continuation passes: same tile, no permutation until the last piece
+            size_t off = 0;
+            const size_t total = pp.rounds.size();
+            while (off < total) {
+                const size_t cnt = std::min((size_t)cfg.max_rounds, total - off);
+                PlanPass piece = pp;
+                piece.rounds.assign(pp.rounds.begin() + off, pp.rounds.begin() + off + cnt);
+                piece.has_phase = pp.has_phase && off == 0;
+                if (off + cnt < total) {
+                    for (int b = 0; b < kMaxQ; ++b) piece.out_of_in[b] = b;
+                    piece.n_shared = TB;
+                }
+                piece.ngates = 0;
+                for (auto& r : piece.rounds) piece.ngates += r.ngates;
+                out.push_back(std::move(piece));
+                off += cnt;
+            }
+        }
+        plan.passes.swap(out);
+    }
+    return plan;
+}
+
+std::string plan_to_json(const Plan& plan) {
+    std::ostringstream os;
+    os.precision(17);
+    os << "{\"nq\":" << plan.nq << ",\"TB\":" << plan.TB << ",\"RB\":" << plan.RB
+       << ",\"total_gates\":" << plan.total_gates << ",\"total_rounds\":" << plan.total_rounds
+       << ",\"layers1_equiv\":" << plan.layers1_equiv << ",\"trailing_ztau\":" << plan.trailing_ztau
+       << ",\"start_perm\":[";
+    for (size_t i = 0; i < plan.start_perm.size(); ++i) os << (i ? "," : "") << plan.start_perm[i];
+    os << "],\"passes\":[";
+    for (size_t p = 0; p < plan.passes.size(); ++p) {
+        const PlanPass& pp = plan.passes[p];
+        os << (p ? "," : "") << "{\"tileq\":[";
+        for (int k = 0; k < plan.TB; ++k) os << (k ? "," : "") << pp.tileq[k];
+        os << "],\"out_of_in\":[";
+        for (int k = 0; k < plan.nq; ++k) os << (k ? "," : "") << pp.out_of_in[k];
+        os << "],\"n_shared\":" << pp.n_shared << ",\"has_phase\":" << (pp.has_phase ? 1 : 0)
+           << ",\"ztau\":" << pp.ztau << ",\"ngates\":" << pp.ngates << ",\"rounds\":[";
+        for (size_t r = 0; r < pp.rounds.size(); ++r) {
+            const PlanRound& pr = pp.rounds[r];
+            os << (r ? "," : "") << "{\"regq\":[";
+            for (int k = 0; k < plan.RB; ++k) os << (k ? "," : "") << pr.regq[k];
+            os << "],\"regpos\":[";
+            for (int k = 0; k < plan.RB; ++k) os << (k ? "," : "") << pr.regpos[k];
+            os << "],\"thrpos\":[";
+            for (int k = 0; k < plan.TB - plan.RB; ++k) os << (k ? "," : "") << pr.thrpos[k];
+            os << "],\"mask\":" << pr.mask << ",\"gates\":[";
+            bool firstg = true;
+            int slot = 0;
+            for (int a = 0; a < plan.RB; ++a)
+                for (int b = a + 1; b < plan.RB; ++b, ++slot)
+                    if ((pr.mask >> slot) & 1) {
+                        os << (firstg ? "" : ",") << "[" << pr.regq[a] << "," << pr.regq[b] << ","
+                           << pr.phi[slot] << "]";
+                        firstg = false;
+                    }
+            os << "]}";
+        }
+        os << "]}";
+    }
+    os << "]}";
+    return os.str();
+}
+
+}  // namespace xyk

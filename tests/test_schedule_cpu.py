@@ -1,0 +1,72 @@
+"""The schedule compiler (host C++ inside libxyk.so) checked on the CPU against the oracle:
+executing the compiled passes in their order, with their layouts, must reproduce the reference
+gate order (oracle Mode T) exactly."""
+
+import numpy as np
+import pytest
+
+from oracle import xy_oracle as oc
+from scpn_quantum_control_b200.engine import plan_describe
+from tests.plan_sim import permute_bits, simulate_plan
+
+
+def _check(n, K, omega, delta, order, reps):
+    plan = plan_describe(K, omega, delta, order, reps)
+    K, omega = oc.canonicalise(n, K, omega)
+    z_terms, pair_terms = oc.term_list(K, omega)
+    psi0 = oc.initial_state(omega)
+    ref = oc.evolve_product_formula(psi0.copy(), z_terms, pair_terms, delta, reps, order)
+    got, perm = simulate_plan(plan, psi0, omega)
+    if plan["trailing_ztau"] != 0.0:
+        zt = [(perm[q], float(omega[q])) for q in range(n) if abs(omega[q]) > 1e-15]
+        oc.apply_z_phase(got, zt, plan["trailing_ztau"])
+    assert perm == plan["start_perm"], "program must end in its own start layout"
+    inv = [0] * n
+    for q in range(n):
+        inv[perm[q]] = q
+    back = permute_bits(got, n, inv)
+    assert 1.0 - oc.fidelity(back, ref) < 1e-12
+    assert np.abs(back - ref).max() < 1e-12
+    ngates = sum(len(r["gates"]) for p in plan["passes"] for r in p["rounds"])
+    assert ngates == plan["total_gates"]
+    return plan
+
+
+@pytest.mark.parametrize("n", [12, 13, 14, 16])
+@pytest.mark.parametrize("order", [1, 2])
+def test_all_to_all_plan_matches_reference_order(n, order):
+    K, w = oc.random_problem(n, 100 + n)
+    plan = _check(n, K, w, 0.1, order, 2)
+    npairs = n * (n - 1) // 2
+    assert plan["total_gates"] == (npairs if order == 1 else 2 * npairs - 1) * 2
+
+
+def test_order4_plan():
+    K, w = oc.random_problem(13, 5)
+    _check(13, K, w, 0.1, 4, 1)
+
+
+def test_sparse_ring_plan():
+    n = 14
+    K = oc.ring_K(n)
+    w = np.tile(oc.OMEGA_N_16, 2)[:n]
+    plan = _check(n, K, w, 0.05, 1, 3)
+    assert plan["total_gates"] == 3 * n
+
+
+def test_no_pairs_plan_is_phase_only():
+    n = 13
+    K = np.zeros((n, n))
+    w = np.linspace(0.5, 2.0, n)
+    plan = plan_describe(K, w, 0.1, 2, 2)
+    assert plan["passes"] == []
+    assert plan["trailing_ztau"] == pytest.approx(0.1)
+
+
+def test_shared_low_bits_between_consecutive_tiles():
+    """Every pass must leave >= 3 of its tile qubits on the lowest output bits (>= 128-byte chunks)."""
+    n = 20
+    K, w = oc.random_problem(n, 3)
+    plan = plan_describe(K, w, 0.1, 1, 1)
+    for p in plan["passes"]:
+        assert p["n_shared"] >= 3
