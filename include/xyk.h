@@ -139,8 +139,10 @@ typedef struct {
     int32_t last_rounds;     /* register rounds of the last apply_layers call              */
     int32_t last_gates;      /* pair gates of the last apply_layers call                   */
     int32_t last_layers1;    /* first-order-layer equivalents of the last apply_layers     */
-    float last_pass_ms;      /* CUDA-event time of the passes of the last call (if timing) */
+    float last_pass_ms;      /* CUDA-event time of the whole last apply_layers call (if timing) */
     int32_t timing_enabled;
+    double pass_kernel_ms;   /* sum of per-launch CUDA-event durations of the fused tile pass kernel */
+    int64_t pass_kernel_timed; /* number of launches in that sum (timing enabled only)            */
 } xyk_stats;
 int xyk_get_stats(xyk_handle h, xyk_stats *out);
 int xyk_enable_timing(xyk_handle h, int on);

@@ -40,6 +40,8 @@ class XYKStats(ctypes.Structure):
         ("last_layers1", c_int32),
         ("last_pass_ms", c_float),
         ("timing_enabled", c_int32),
+        ("pass_kernel_ms", c_double),
+        ("pass_kernel_timed", c_int64),
     ]
 
 

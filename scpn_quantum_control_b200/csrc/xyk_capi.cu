@@ -61,6 +61,7 @@ struct xyk_handle_s {
     std::map<std::tuple<uint64_t, int, int, double>, std::shared_ptr<Program>> programs;
     xyk_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> pass_events;  // per-launch timing of the tile pass kernel
     std::string err;
 };
 
@@ -333,10 +334,19 @@ int run_program_tiled(xyk_handle h, Program& prog) {
         }
         const double2* in = (const double2*)h->buf[h->cur];
         double2* out = (double2*)h->buf[h->cur ^ 1];
+        if (h->stats.timing_enabled) {
+            while (h->pass_events.size() < 2 * (p + 1)) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                h->pass_events.push_back(e);
+            }
+            cudaEventRecord(h->pass_events[2 * p], h->stream);
+        }
         if (prog.lift[p])
             tile_pass_kernel<kTB, kRB, true, 3><<<grid, 1 << (kTB - kRB), smem, h->stream>>>(in, out, prog.descs[p], ntiles);
         else
             tile_pass_kernel<kTB, kRB, false, 3><<<grid, 1 << (kTB - kRB), smem, h->stream>>>(in, out, prog.descs[p], ntiles);
+        if (h->stats.timing_enabled) cudaEventRecord(h->pass_events[2 * p + 1], h->stream);
         h->cur ^= 1;
         std::vector<int> np(h->perm);
         for (int q = 0; q < plan.nq; ++q) np[q] = pp.out_of_in[h->perm[q]];
@@ -353,6 +363,12 @@ int run_program_tiled(xyk_handle h, Program& prog) {
         cudaEventRecord(h->ev1, h->stream);
         cudaEventSynchronize(h->ev1);
         cudaEventElapsedTime(&h->stats.last_pass_ms, h->ev0, h->ev1);
+        for (size_t p = 0; p < plan.passes.size(); ++p) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->pass_events[2 * p], h->pass_events[2 * p + 1]);
+            h->stats.pass_kernel_ms += ms;
+            h->stats.pass_kernel_timed++;
+        }
     }
     XYK_CUDA(h, cudaGetLastError());
     h->stats.last_passes = (int)plan.passes.size();
@@ -480,6 +496,7 @@ int xyk_destroy(xyk_handle h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t e : h->pass_events) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return XYK_OK;
