@@ -228,19 +228,37 @@ int relayout(xyk_handle h, const std::vector<int>& target) {
     return XYK_OK;
 }
 
-void fill_desc(const Plan& plan, const PlanPass& pp, Desc& d, bool& lift_ok) {
+void fill_desc(xyk_handle h, const Plan& plan, const PlanPass& pp, const std::vector<int>& perm_in, Desc& d,
+               bool& lift_ok) {
     std::memset(&d, 0, sizeof(d));
     d.nq = plan.nq;
     d.nrounds = (int)pp.rounds.size();
-    d.has_phase = 0;
+    d.flags = (pp.fuse_load ? kPassFuseLoad : 0u) | (pp.fuse_store ? kPassFuseStore : 0u);
     for (int b = 0; b + kTB < plan.nq; ++b) d.hi_out[b] = (uint8_t)pp.out_of_in[kTB + b];
-    // tile bits ordered by their output position
+    // tile bits ordered by their output position (unfused store)
     int order[kTB];
     for (int k = 0; k < kTB; ++k) order[k] = k;
     std::sort(order, order + kTB, [&](int a, int b) { return pp.out_of_in[a] < pp.out_of_in[b]; });
     for (int m = 0; m < kTB; ++m) {
         d.st_lsrc[m] = (uint8_t)order[m];
         d.st_odst[m] = (uint8_t)pp.out_of_in[order[m]];
+    }
+    const PlanRound& last = pp.rounds.back();
+    for (int b = 0; b < Desc::NT; ++b) d.last_thr_out[b] = (uint8_t)pp.out_of_in[last.thrpos[b]];
+    for (int k = 0; k < kRB; ++k) d.last_reg_out[k] = (uint8_t)pp.out_of_in[last.regpos[k]];
+    // fused diagonal phase: weights per INPUT physical bit, register table of round 0
+    if (pp.has_phase && h->fuse_phase && !h->zterms.empty()) {
+        d.flags |= kPassHasPhase;
+        d.ph_tau = pp.ztau;
+        std::vector<double> wq(plan.nq, 0.0);
+        for (const auto& z : h->zterms) wq[z.i] = z.w;
+        for (int q = 0; q < plan.nq; ++q) d.ph_w[perm_in[q]] = wq[q];
+        const PlanRound& r0 = pp.rounds.front();
+        for (int j = 0; j < (1 << kRB); ++j) {
+            double ph = 0.0;
+            for (int k = 0; k < kRB; ++k) ph += d.ph_w[r0.regpos[k]] * (((j >> k) & 1) ? -1.0 : 1.0);
+            d.ph_reg[j] = make_double2(std::cos(pp.ztau * ph), std::sin(pp.ztau * ph));
+        }
     }
     lift_ok = true;
     for (int r = 0; r < d.nrounds; ++r) {
@@ -255,7 +273,13 @@ void fill_desc(const Plan& plan, const PlanPass& pp, Desc& d, bool& lift_ok) {
         const PlanRound& pr = pp.rounds[r];
         Desc::Round& R = d.rounds[r];
         for (int b = 0; b < Desc::NT; ++b) R.thrpos[b] = (uint8_t)pr.thrpos[b];
-        for (int k = 0; k < kRB; ++k) R.regpos[k] = (uint8_t)pr.regpos[k];
+        for (int k = 0; k < kRB; ++k) {
+            R.regpos[k] = (uint8_t)pr.regpos[k];
+            const uint32_t x = 1u << pr.regpos[k];
+            uint32_t sw = x;
+            if (pr.regpos[k] >= 3) sw ^= (uint32_t)swizzle_vec(pr.regpos[k]);
+            R.regsw[k] = (uint16_t)sw;
+        }
         R.mask = pr.mask;
         for (int s = 0; s < Desc::NSLOT; ++s) {
             if (!((pr.mask >> s) & 1u)) continue;
@@ -272,7 +296,7 @@ void fill_desc(const Plan& plan, const PlanPass& pp, Desc& d, bool& lift_ok) {
 }
 
 std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int reps) {
-    const auto key = std::make_tuple(h->problem_version, order, reps, delta);
+    const auto key = std::make_tuple(h->problem_version * 2 + (uint64_t)(h->fuse_phase ? 1 : 0), order, reps, delta);
     auto it = h->programs.find(key);
     if (it != h->programs.end()) return it->second;
     auto prog = std::make_shared<Program>();
@@ -287,10 +311,14 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
     prog->plan.layers1_equiv = l1;
     prog->descs.resize(prog->plan.passes.size());
     prog->lift.resize(prog->plan.passes.size());
+    std::vector<int> perm(prog->plan.start_perm);
     for (size_t p = 0; p < prog->plan.passes.size(); ++p) {
         bool lift = true;
-        fill_desc(prog->plan, prog->plan.passes[p], prog->descs[p], lift);
+        fill_desc(h, prog->plan, prog->plan.passes[p], perm, prog->descs[p], lift);
         prog->lift[p] = lift ? 1 : 0;
+        std::vector<int> np(perm);
+        for (int q = 0; q < prog->plan.nq; ++q) np[q] = prog->plan.passes[p].out_of_in[perm[q]];
+        perm.swap(np);
     }
     if (h->programs.size() > 64) h->programs.clear();
     h->programs[key] = prog;
@@ -328,7 +356,7 @@ int run_program_tiled(xyk_handle h, Program& prog) {
     if (h->stats.timing_enabled) cudaEventRecord(h->ev0, h->stream);
     for (size_t p = 0; p < plan.passes.size(); ++p) {
         const PlanPass& pp = plan.passes[p];
-        if (pp.has_phase) {
+        if (pp.has_phase && !(prog.descs[p].flags & kPassHasPhase)) {
             rc = apply_phase(h, pp.ztau);
             if (rc) return rc;
         }

@@ -58,6 +58,8 @@ struct PlanPass {
     bool has_phase;                // diagonal phase exp(+i ztau sum w_q (1-2b_q)) applied before the gates
     double ztau;
     bool std_rot;                  // some angle too large for the shear (lifting) form
+    bool fuse_load;                // round 0 can read global memory directly (coalesced lane mapping exists)
+    bool fuse_store;               // the last round can write global memory directly
     int ngates;
 };
 
@@ -77,6 +79,8 @@ struct SchedConfig {
     int RB = 5;            // register bits (amplitudes per thread = 2^RB)
     int need_shared = 3;   // consecutive tiles must share this many qubits (contiguous output chunks)
     int max_rounds = 14;   // rounds a single pass descriptor can carry
+    int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
+    bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
 };
 
 // Compile the segments into tile passes over nq local qubits.  Throws std::runtime_error.

@@ -327,25 +327,35 @@ __global__ void convert_kernel(const typename cplx<from>::type* __restrict__ src
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxRounds = 14;
 
+constexpr uint32_t kPassFuseLoad = 1u;   // round 0 reads its amplitudes straight from global memory
+constexpr uint32_t kPassFuseStore = 2u;  // the last round writes its amplitudes straight to global memory
+constexpr uint32_t kPassHasPhase = 4u;   // diagonal phase folded into round 0
+
 template <int TB, int RB>
 struct PassDesc {
     static constexpr int NT = TB - RB;
     static constexpr int NSLOT = RB * (RB - 1) / 2;
     struct Round {
-        uint8_t thrpos[8];  // tile-local position of thread bit b (NT used)
-        uint8_t regpos[8];  // tile-local position of register bit k (RB used)
-        uint32_t mask;      // enabled pair slots
+        uint8_t thrpos[8];   // tile-local position of thread bit b (NT used)
+        uint8_t regpos[8];   // tile-local position of register bit k (RB used)
+        uint16_t regsw[8];   // swizzled shared-memory slot offset of register bit k
+        uint32_t mask;       // enabled pair slots
         uint32_t pad;
-        double ca[NSLOT];   // shear form: -tan(phi/2); standard form: cos(phi)
-        double cb[NSLOT];   // sin(phi)
+        double ca[NSLOT];    // shear form: -tan(phi/2); standard form: cos(phi)
+        double cb[NSLOT];    // sin(phi)
     };
-    int32_t nq;             // local qubits
+    int32_t nq;              // local qubits
     int32_t nrounds;
-    int32_t has_phase;
+    uint32_t flags;
     int32_t pad0;
-    uint8_t hi_out[kMaxQ];  // output bit of input bit TB + b (the tile-id bits)
-    uint8_t st_lsrc[16];    // tile-local position of the tile bit with the m-th smallest output bit
-    uint8_t st_odst[16];    // that output bit
+    uint8_t hi_out[kMaxQ];   // output bit of input bit TB + b (the tile-id bits)
+    uint8_t st_lsrc[16];     // unfused store: tile-local position of the tile bit with the m-th smallest output bit
+    uint8_t st_odst[16];     //                that output bit
+    uint8_t last_thr_out[8]; // fused store: output bit of the qubit on thread bit b of the LAST round
+    uint8_t last_reg_out[8]; //              output bit of the qubit on register bit k of the LAST round
+    double ph_tau;           // fused phase: exp(+i tau sum_b w_b (1 - 2 bit_b)) over all input bits
+    double ph_w[kMaxQ];      // omega of the logical qubit on INPUT physical bit b
+    double2 ph_reg[1 << RB]; // phase factor of register index j in round 0
     Round rounds[kMaxRounds];
 };
 
@@ -363,58 +373,126 @@ __device__ __forceinline__ void rotate2(double& x, double& y, double ca, double 
     }
 }
 
+// One pass = one read + one write of the state.  Per tile (2^TB consecutive amplitudes of the
+// input buffer): round 0 pulls 2^RB amplitudes per thread (straight from global memory when the
+// schedule allows a coalesced mapping, else through a cp.async staged tile), every round applies
+// the enabled rotations among its RB register qubits and exchanges through swizzled shared
+// memory, and the last round scatters the result through the output bit permutation (straight
+// from registers when the schedule allows, else through shared memory).
 template <int TB, int RB, bool LIFT, int MINB>
 __global__ void __launch_bounds__(1 << (TB - RB), MINB)
 tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                  const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles) {
     constexpr int NT = TB - RB, NREG = 1 << RB;
+    using Round = typename PassDesc<TB, RB>::Round;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* tile = reinterpret_cast<double2*>(smem_raw);
     const uint32_t tid = threadIdx.x;
+    const uint32_t flags = P.flags;
+    const int nr = P.nrounds;
 
-    // per-thread constants of the load and store phases
+    // per-thread constants of the (unfused) load and store phases
     const uint32_t ld_slot = swz<TB>(tid);  // index bits [0, NT) <- thread id
     uint32_t st_l = 0;
     uint64_t st_d = 0;
+    if (flags & kPassFuseStore) {
 #pragma unroll
-    for (int b = 0; b < NT; ++b)
-        if ((tid >> b) & 1u) {
-            st_l |= 1u << P.st_lsrc[b];
-            st_d |= 1ull << P.st_odst[b];
+        for (int b = 0; b < NT; ++b)
+            if ((tid >> b) & 1u) st_d |= 1ull << P.last_thr_out[b];
+    } else {
+#pragma unroll
+        for (int b = 0; b < NT; ++b)
+            if ((tid >> b) & 1u) {
+                st_l |= 1u << P.st_lsrc[b];
+                st_d |= 1ull << P.st_odst[b];
+            }
+        st_l = swz<TB>(st_l);
+    }
+    // fused phase: contribution of this thread's round-0 index bits
+    double ph_thr = 0.0;
+    if (flags & kPassHasPhase) {
+#pragma unroll
+        for (int b = 0; b < NT; ++b) {
+            const double wv = P.ph_w[P.rounds[0].thrpos[b]];
+            ph_thr += ((tid >> b) & 1u) ? -wv : wv;
         }
-    st_l = swz<TB>(st_l);
+    }
 
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        // ---- load: the tile is one contiguous run of 2^TB amplitudes ----
+        __syncthreads();  // every warp is done reading the previous tile out of shared memory
         const double2* src = in + (t << TB);
-#pragma unroll
-        for (int k = 0; k < NREG; ++k) {
-            const uint32_t hi = swz<TB>((uint32_t)k << NT);  // compile-time constant after unrolling
-            cp_async16(&tile[ld_slot ^ hi], src + ((uint32_t)k << NT) + tid);
-        }
-        cp_async_wait_all();
-        __syncthreads();
+        uint64_t obase = 0;
+        for (int b = 0; b < P.nq - TB; ++b)
+            if ((t >> b) & 1ull) obase |= 1ull << P.hi_out[b];
 
-        // ---- register rounds ----
-        for (int r = 0; r < P.nrounds; ++r) {
-            const typename PassDesc<TB, RB>::Round& R = P.rounds[r];
-            uint32_t base = 0;
+        for (int r = 0; r < nr; ++r) {
+            const Round& R = P.rounds[r];
+            uint32_t lin = 0;
 #pragma unroll
             for (int b = 0; b < NT; ++b)
-                if ((tid >> b) & 1u) base |= 1u << R.thrpos[b];
-            base = swz<TB>(base);
+                if ((tid >> b) & 1u) lin |= 1u << R.thrpos[b];
+            const uint32_t base = swz<TB>(lin);
             uint32_t rb[RB];
 #pragma unroll
-            for (int k = 0; k < RB; ++k) rb[k] = swz<TB>(1u << R.regpos[k]);
+            for (int k = 0; k < RB; ++k) rb[k] = R.regsw[k];
             double2 a[NREG];
+
+            if (r == 0) {
+                if (flags & kPassFuseLoad) {
+                    const double2* p0 = src + lin;
 #pragma unroll
-            for (int j = 0; j < NREG; ++j) {
-                uint32_t off = 0;
+                    for (int j = 0; j < NREG; ++j) {
+                        uint32_t off = 0;
 #pragma unroll
-                for (int k = 0; k < RB; ++k)
-                    if ((j >> k) & 1) off ^= rb[k];
-                a[j] = tile[base ^ off];
+                        for (int k = 0; k < RB; ++k)
+                            if ((j >> k) & 1) off += 1u << R.regpos[k];
+                        a[j] = __ldcs(p0 + off);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NREG; ++k) {
+                        const uint32_t hi = swz<TB>((uint32_t)k << NT);  // constant after unrolling
+                        cp_async16(&tile[ld_slot ^ hi], src + ((uint32_t)k << NT) + tid);
+                    }
+                    cp_async_wait_all();
+                    __syncthreads();
+#pragma unroll
+                    for (int j = 0; j < NREG; ++j) {
+                        uint32_t off = 0;
+#pragma unroll
+                        for (int k = 0; k < RB; ++k)
+                            if ((j >> k) & 1) off ^= rb[k];
+                        a[j] = tile[base ^ off];
+                    }
+                }
+                if (flags & kPassHasPhase) {
+                    double ph = ph_thr;
+                    for (int b = 0; b < P.nq - TB; ++b) {
+                        const double wv = P.ph_w[TB + b];
+                        ph += ((t >> b) & 1ull) ? -wv : wv;
+                    }
+                    double sn, cs;
+                    sincos(P.ph_tau * ph, &sn, &cs);
+#pragma unroll
+                    for (int j = 0; j < NREG; ++j) {
+                        const double2 f = P.ph_reg[j];
+                        const double fr = cs * f.x - sn * f.y, fi = cs * f.y + sn * f.x;
+                        const double xr = a[j].x, xi = a[j].y;
+                        a[j].x = xr * fr - xi * fi;
+                        a[j].y = xr * fi + xi * fr;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NREG; ++j) {
+                    uint32_t off = 0;
+#pragma unroll
+                    for (int k = 0; k < RB; ++k)
+                        if ((j >> k) & 1) off ^= rb[k];
+                    a[j] = tile[base ^ off];
+                }
             }
+
             const uint32_t mask = R.mask;
 #pragma unroll
             for (int x = 0; x < RB; ++x) {
@@ -433,35 +511,46 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     }
                 }
             }
+
+            if (r == nr - 1 && (flags & kPassFuseStore)) {
+                double2* dst = out + obase + st_d;
 #pragma unroll
-            for (int j = 0; j < NREG; ++j) {
-                uint32_t off = 0;
+                for (int j = 0; j < NREG; ++j) {
+                    uint64_t off = 0;
 #pragma unroll
-                for (int k = 0; k < RB; ++k)
-                    if ((j >> k) & 1) off ^= rb[k];
-                tile[base ^ off] = a[j];
+                    for (int k = 0; k < RB; ++k)
+                        if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
+                    __stcs(dst + off, a[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NREG; ++j) {
+                    uint32_t off = 0;
+#pragma unroll
+                    for (int k = 0; k < RB; ++k)
+                        if ((j >> k) & 1) off ^= rb[k];
+                    tile[base ^ off] = a[j];
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
 
-        // ---- store through the bit permutation ----
-        uint64_t obase = 0;
-        for (int b = 0; b < P.nq - TB; ++b)
-            if ((t >> b) & 1ull) obase |= 1ull << P.hi_out[b];
-        double2* dst = out + obase + st_d;
+        if (!(flags & kPassFuseStore)) {
+            // ---- store through the bit permutation, staged in shared memory ----
+            double2* dst = out + obase + st_d;
 #pragma unroll
-        for (int k = 0; k < NREG; ++k) {
-            uint32_t lk = 0;
-            uint64_t dk = 0;
+            for (int k = 0; k < NREG; ++k) {
+                uint32_t lk = 0;
+                uint64_t dk = 0;
 #pragma unroll
-            for (int b = 0; b < RB; ++b)
-                if ((k >> b) & 1) {
-                    lk |= 1u << P.st_lsrc[NT + b];
-                    dk |= 1ull << P.st_odst[NT + b];
-                }
-            dst[dk] = tile[st_l ^ swz<TB>(lk)];
+                for (int b = 0; b < RB; ++b)
+                    if ((k >> b) & 1) {
+                        lk |= 1u << P.st_lsrc[NT + b];
+                        dk |= 1ull << P.st_odst[NT + b];
+                    }
+                __stcs(dst + dk, tile[st_l ^ swz<TB>(lk)]);
+            }
         }
-        __syncthreads();
     }
 }
 

@@ -310,31 +310,162 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         if (raw.empty()) first_tile = 0;
     }
 
-    // ---- 2. layouts: tile qubits of pass p sit on physical bits [0, TB) before pass p ----
-    // layout_of(p): shared qubits with the previous tile first (ascending), then the other tile
-    // qubits ascending, then every other qubit ascending.
+    // ---- 2. register rounds of every pass (sets of RB qubits + the gates they execute) ----
+    // The LAST round of a pass is chosen first (closure over the reversed sequence) and the FIRST
+    // round next, both with a cap on how many qubits shared with the neighbouring tile they may
+    // hold in registers: the qubits that stay out of both become the lowest physical bits of the
+    // layout between the two passes, which lets the last round store and the next first round
+    // load global memory directly with lanes on contiguous addresses.
     const int P = (int)raw.size();
-    auto make_layout = [&](uint64_t tile, uint64_t prev, std::vector<int>& perm, int& nshared) {
+    struct RawRound {
+        uint64_t rmask = 0;
+        std::vector<int> cidx;  // indices into the pass's gate_idx
+        bool reverse = false;
+    };
+    std::vector<std::vector<RawRound>> rr(P);
+    std::vector<uint64_t> rlast(P, 0), rfirst(P, 0);
+    const int c_lane = std::min(cfg.lane_bits, TB);
+
+    auto rev_round_closure = [&](const std::vector<Gate>& g, const std::vector<int>& cand,
+                                 const std::vector<char>& cdone, uint64_t rmask, std::vector<int>& out) {
+        out.clear();
+        uint64_t blocked = 0;
+        int sweep = -1;
+        for (int c = (int)cand.size() - 1; c >= 0; --c) {
+            if (cdone[c]) continue;
+            const Gate& q = g[cand[c]];
+            const uint64_t m = (1ull << q.i) | (1ull << q.j);
+            const bool fits = (m & rmask) == m && !(m & blocked) && (sweep < 0 || q.sweep == sweep);
+            if (fits) {
+                out.push_back(c);
+                sweep = q.sweep;
+            } else {
+                blocked |= m;
+            }
+            if (popc(rmask & ~blocked) < 2) break;
+        }
+    };
+    // exhaustive search over RB-subsets of the tile; `limit_mask`/`limit` cap |R & limit_mask|;
+    // `prefer` breaks ties towards subsets overlapping it (keeps the union with a neighbour small)
+    auto search_round = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cdone,
+                            bool reverse_scan, uint64_t limit_mask, int limit, uint64_t prefer, RawRound& best) {
+        std::vector<int> tq;
+        for (int q = 0; q < nq; ++q)
+            if ((rp.tmask >> q) & 1) tq.push_back(q);
+        const int tn = (int)tq.size();
+        std::vector<int> idx(RB), ex;
+        for (int k = 0; k < RB; ++k) idx[k] = k;
+        best.rmask = 0;
+        best.cidx.clear();
+        int best_pref = -1;
+        while (true) {
+            uint64_t rm = 0;
+            for (int k = 0; k < RB; ++k) rm |= 1ull << tq[idx[k]];
+            if (popc(rm & limit_mask) <= limit) {
+                if (reverse_scan) rev_round_closure(g, rp.gate_idx, cdone, rm, ex);
+                else round_closure(g, rp.gate_idx, cdone, rm, ex);
+                const int pref = popc(rm & prefer);
+                if (ex.size() > best.cidx.size() || (ex.size() == best.cidx.size() && !ex.empty() && pref > best_pref)) {
+                    best.cidx = ex;
+                    best.rmask = rm;
+                    best_pref = pref;
+                }
+            }
+            int k = RB - 1;
+            while (k >= 0 && idx[k] == tn - RB + k) --k;
+            if (k < 0) break;
+            ++idx[k];
+            for (int m = k + 1; m < RB; ++m) idx[m] = idx[m - 1] + 1;
+        }
+        if (!best.cidx.empty()) {
+            best.reverse = g[rp.gate_idx[best.cidx[0]]].reverse;
+            std::sort(best.cidx.begin(), best.cidx.end());
+        }
+    };
+
+    std::vector<std::vector<char>> cdone(P);
+    std::vector<RawRound> last_round(P), first_round(P);
+    std::vector<char> single_round(P, 0);
+    for (int p = 0; p < P; ++p) cdone[p].assign(raw[p].gate_idx.size(), 0);
+    // (a) last rounds
+    for (int p = 0; p < P; ++p) {
+        const RawPass& rp = raw[p];
+        const std::vector<Gate>& g = sg[rp.seg];
+        const uint64_t shared_next = P == 1 ? 0 : (rp.tmask & raw[(p + 1) % P].tmask);
+        const int s = popc(shared_next);
+        RawRound best;
+        if (cfg.fuse_io && s - c_lane >= 1) {
+            const int budget = (s - c_lane + 1) / 2;
+            search_round(rp, g, cdone[p], true, shared_next, budget, 0, best);
+        }
+        if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
+        if (best.cidx.empty()) throw std::runtime_error("compile_plan: last-round search made no progress");
+        for (int c : best.cidx) cdone[p][c] = 1;
+        rlast[p] = best.rmask;
+        last_round[p] = best;
+    }
+    // (b) first rounds, (c) middle rounds
+    for (int p = 0; p < P; ++p) {
+        const RawPass& rp = raw[p];
+        const std::vector<Gate>& g = sg[rp.seg];
+        size_t ndone = last_round[p].cidx.size();
+        if (ndone == rp.gate_idx.size()) {
+            single_round[p] = 1;
+            rfirst[p] = rlast[p];
+            continue;
+        }
+        const int pm = (p + P - 1) % P;
+        const uint64_t shared_prev = P == 1 ? 0 : (rp.tmask & raw[pm].tmask);
+        const int budget = popc(shared_prev) - c_lane - popc(rlast[pm] & shared_prev);
+        RawRound best;
+        if (cfg.fuse_io && budget >= 0) search_round(rp, g, cdone[p], false, shared_prev, budget, rlast[pm], best);
+        if (best.cidx.empty()) search_round(rp, g, cdone[p], false, 0, 99, rlast[pm], best);
+        if (best.cidx.empty()) throw std::runtime_error("compile_plan: first-round search made no progress");
+        for (int c : best.cidx) cdone[p][c] = 1;
+        ndone += best.cidx.size();
+        rfirst[p] = best.rmask;
+        first_round[p] = best;
+        rr[p].push_back(best);
+        while (ndone < rp.gate_idx.size()) {
+            RawRound mid;
+            search_round(rp, g, cdone[p], false, 0, 99, 0, mid);
+            if (mid.cidx.empty()) throw std::runtime_error("compile_plan: round search made no progress");
+            for (int c : mid.cidx) cdone[p][c] = 1;
+            ndone += mid.cidx.size();
+            rr[p].push_back(mid);
+        }
+    }
+    for (int p = 0; p < P; ++p) rr[p].push_back(last_round[p]);
+
+    // ---- 3. layouts: tile qubits of pass p sit on physical bits [0, TB) before pass p ----
+    // order: qubits shared with the previous tile that neither the previous last round nor this
+    // first round holds in registers (-> lanes of the fused global I/O), then the other shared
+    // qubits, then the remaining tile qubits, then everything else; ascending inside each class.
+    auto make_layout = [&](int p, std::vector<int>& perm, int& nshared, int& nfree) {
+        const uint64_t tile = raw[p].tmask;
+        const int pm = (p + P - 1) % P;
+        const uint64_t prev = P == 1 ? 0 : raw[pm].tmask;
         perm.assign(nq, -1);
         int pos = 0;
         const uint64_t shared = tile & prev;
+        const uint64_t avoid = P == 1 ? 0 : (rlast[pm] | rfirst[p]);
         nshared = popc(shared);
-        for (int q = 0; q < nq; ++q)
-            if ((shared >> q) & 1) perm[q] = pos++;
-        for (int q = 0; q < nq; ++q)
-            if (((tile & ~shared) >> q) & 1) perm[q] = pos++;
+        nfree = popc(shared & ~avoid);
+        const uint64_t classes[5] = {shared & ~avoid, shared & rlast[pm] & ~rfirst[p], shared & rfirst[p] & ~rlast[pm],
+                                     shared & rfirst[p] & rlast[pm], tile & ~shared};
+        for (uint64_t cls : classes)
+            for (int q = 0; q < nq; ++q)
+                if ((cls >> q) & 1) perm[q] = pos++;
         for (int q = 0; q < nq; ++q)
             if (!((tile >> q) & 1)) perm[q] = pos++;
     };
     std::vector<std::vector<int>> layouts(P + 1);
-    std::vector<int> nshared(P + 1, 0);
-    for (int p = 0; p < P; ++p) {
-        const uint64_t prev = p == 0 ? raw[P - 1].tmask : raw[p - 1].tmask;
-        make_layout(raw[p].tmask, P == 1 ? 0 : prev, layouts[p], nshared[p]);
-    }
+    std::vector<int> nshared(P + 1, 0), nfree(P + 1, 0);
+    for (int p = 0; p < P; ++p) make_layout(p, layouts[p], nshared[p], nfree[p]);
     if (P > 0) {
         layouts[P] = layouts[0];
         nshared[P] = nshared[0];
+        nfree[P] = nfree[0];
         plan.start_perm = layouts[0];
         plan.end_perm = layouts[0];
     } else {
@@ -343,8 +474,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         plan.end_perm = plan.start_perm;
     }
 
-    // ---- 3. rounds of every pass ----
-    std::vector<int> subset(RB);
+    // ---- 4. emit passes ----
     for (int p = 0; p < P; ++p) {
         const RawPass& rp = raw[p];
         const std::vector<Gate>& g = sg[rp.seg];
@@ -353,63 +483,48 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         std::memset(pp.tileq, -1, sizeof(pp.tileq));
         const std::vector<int>& lay = layouts[p];
         int qpos[64];
+        std::vector<int> inv(nq);
         for (int q = 0; q < nq; ++q) {
             qpos[q] = lay[q];
+            inv[lay[q]] = q;
             if (lay[q] < TB) pp.tileq[lay[q]] = q;
         }
         for (int b = 0; b < kMaxQ; ++b) pp.out_of_in[b] = b;
-        {
-            std::vector<int> inv(nq);
-            for (int q = 0; q < nq; ++q) inv[lay[q]] = q;
-            for (int b = 0; b < nq; ++b) pp.out_of_in[b] = layouts[p + 1][inv[b]];
-        }
-        pp.n_shared = nshared[p + 1];
-        if (P == 1) pp.n_shared = TB;
+        for (int b = 0; b < nq; ++b) pp.out_of_in[b] = layouts[p + 1][inv[b]];
+        pp.n_shared = P == 1 ? TB : nshared[p + 1];
         pp.has_phase = rp.has_phase && zeff[rp.seg] != 0.0;
         pp.ztau = pp.has_phase ? zeff[rp.seg] : 0.0;
         pp.std_rot = false;
         pp.ngates = (int)rp.gate_idx.size();
-
-        std::vector<char> cdone(rp.gate_idx.size(), 0);
-        size_t ndone = 0;
-        std::vector<int> ex, bestex;
-        std::vector<int> tq;  // tile qubits
-        for (int q = 0; q < nq; ++q)
-            if ((rp.tmask >> q) & 1) tq.push_back(q);
-        const int tn = (int)tq.size();
-        while (ndone < rp.gate_idx.size()) {
-            // exhaustive search over RB-subsets of the tile qubits
-            uint64_t bestmask = 0;
-            bestex.clear();
-            std::vector<int> idx(RB);
-            for (int k = 0; k < RB; ++k) idx[k] = k;
-            while (true) {
-                uint64_t rm = 0;
-                for (int k = 0; k < RB; ++k) rm |= 1ull << tq[idx[k]];
-                round_closure(g, rp.gate_idx, cdone, rm, ex);
-                if (ex.size() > bestex.size()) {
-                    bestex = ex;
-                    bestmask = rm;
-                }
-                int k = RB - 1;
-                while (k >= 0 && idx[k] == tn - RB + k) --k;
-                if (k < 0) break;
-                ++idx[k];
-                for (int m = k + 1; m < RB; ++m) idx[m] = idx[m - 1] + 1;
+        const int nrounds = (int)rr[p].size();
+        // fused global I/O is possible when the lowest c_lane physical bits (before / after the
+        // pass) carry qubits that the first / last round does not hold in registers
+        bool fl = cfg.fuse_io && nq > TB, fs = cfg.fuse_io && nq > TB;
+        for (int b = 0; b < c_lane && fl; ++b) fl = !((rfirst[p] >> inv[b]) & 1);
+        {
+            std::vector<int> inv_next(nq);
+            for (int q = 0; q < nq; ++q) inv_next[layouts[p + 1][q]] = q;
+            for (int b = 0; b < c_lane && fs; ++b) {
+                const int q = inv_next[b];
+                fs = ((rp.tmask >> q) & 1) && !((rlast[p] >> q) & 1);
             }
-            if (bestex.empty()) throw std::runtime_error("compile_plan: round search made no progress");
+        }
+        if (nrounds == 1 && fl) fs = false;  // one round cannot serve both lane mappings
+        pp.fuse_load = fl;
+        pp.fuse_store = fs;
+
+        for (int r = 0; r < nrounds; ++r) {
+            const RawRound& R = rr[p][r];
             PlanRound pr;
             std::memset(&pr, 0, sizeof(pr));
-            const bool rev = g[rp.gate_idx[bestex[0]]].reverse;
             std::vector<int> rq;
             for (int q = 0; q < nq; ++q)
-                if ((bestmask >> q) & 1) rq.push_back(q);
-            if (rev) std::reverse(rq.begin(), rq.end());
+                if ((R.rmask >> q) & 1) rq.push_back(q);
+            if (R.reverse) std::reverse(rq.begin(), rq.end());
             for (int k = 0; k < RB; ++k) {
                 pr.regq[k] = rq[k];
                 pr.regpos[k] = qpos[rq[k]];
             }
-            // thread bits: three positions with linearly independent swizzle vectors first
             std::vector<int> freepos;
             for (int pos = 0; pos < TB; ++pos) {
                 bool isreg = false;
@@ -418,7 +533,13 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             }
             const int nthr = (int)freepos.size();
             std::vector<int> order;
-            {
+            if (r == 0 && fl) {
+                order = freepos;  // ascending: lanes 0.. sit on the lowest physical bits
+            } else if (r == nrounds - 1 && fs) {
+                order = freepos;  // ascending OUTPUT position: lanes 0.. write contiguous addresses
+                std::sort(order.begin(), order.end(), [&](int a, int b) { return pp.out_of_in[a] < pp.out_of_in[b]; });
+            } else {
+                // three positions with linearly independent swizzle vectors first (bank-conflict free)
                 int pick[3] = {-1, -1, -1};
                 bool found = false;
                 for (int a = 0; a < nthr && !found; ++a)
@@ -441,8 +562,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                     if (!used[a]) order.push_back(freepos[a]);
             }
             for (int b = 0; b < nthr; ++b) pr.thrpos[b] = order[b];
-            // slots
-            for (int c : bestex) {
+            for (int c : R.cidx) {
                 const Gate& q = g[rp.gate_idx[c]];
                 int a = -1, b = -1;
                 for (int k = 0; k < RB; ++k) {
@@ -451,16 +571,14 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                         else b = k;
                     }
                 }
-                // slot index of (a, b), a < b, lexicographic
                 int slot = 0;
                 for (int x = 0; x < a; ++x) slot += RB - 1 - x;
                 slot += b - a - 1;
+                if ((pr.mask >> slot) & 1u) throw std::runtime_error("compile_plan: pair scheduled twice in one round");
                 pr.mask |= 1u << slot;
                 pr.phi[slot] = gop[rp.gate_idx[c]].phi;
-                cdone[c] = 1;
             }
-            pr.ngates = (int)bestex.size();
-            ndone += bestex.size();
+            pr.ngates = (int)R.cidx.size();
             pp.rounds.push_back(pr);
         }
         plan.total_gates += pp.ngates;
@@ -483,6 +601,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 PlanPass piece = pp;
                 piece.rounds.assign(pp.rounds.begin() + off, pp.rounds.begin() + off + cnt);
                 piece.has_phase = pp.has_phase && off == 0;
+                piece.fuse_load = pp.fuse_load && off == 0;
+                piece.fuse_store = pp.fuse_store && off + cnt == total;
                 if (off + cnt < total) {
                     for (int b = 0; b < kMaxQ; ++b) piece.out_of_in[b] = b;
                     piece.n_shared = TB;
@@ -514,7 +634,8 @@ std::string plan_to_json(const Plan& plan) {
         os << "],\"out_of_in\":[";
         for (int k = 0; k < plan.nq; ++k) os << (k ? "," : "") << pp.out_of_in[k];
         os << "],\"n_shared\":" << pp.n_shared << ",\"has_phase\":" << (pp.has_phase ? 1 : 0)
-           << ",\"ztau\":" << pp.ztau << ",\"ngates\":" << pp.ngates << ",\"rounds\":[";
+           << ",\"ztau\":" << pp.ztau << ",\"ngates\":" << pp.ngates << ",\"fuse_load\":" << (pp.fuse_load ? 1 : 0)
+           << ",\"fuse_store\":" << (pp.fuse_store ? 1 : 0) << ",\"rounds\":[";
         for (size_t r = 0; r < pp.rounds.size(); ++r) {
             const PlanRound& pr = pp.rounds[r];
             os << (r ? "," : "") << "{\"regq\":[";
