@@ -281,6 +281,7 @@ void fill_desc(xyk_handle h, const Plan& plan, const PlanPass& pp, const std::ve
             R.regsw[k] = (uint16_t)sw;
         }
         R.mask = pr.mask;
+        R.cta_sync = (uint32_t)pr.cta_sync_after;
         for (int s = 0; s < Desc::NSLOT; ++s) {
             if (!((pr.mask >> s) & 1u)) continue;
             const double phi = std::remainder(pr.phi[s], 2.0 * M_PI);

@@ -48,6 +48,7 @@ struct PlanRound {
     uint32_t mask;    // enabled pair slots, slot order = lexicographic (a, b), a < b over register bits
     double phi[16];   // angle per slot (only enabled slots are meaningful)
     int ngates;
+    int cta_sync_after;  // 1: block-wide barrier after this round's exchange, 0: the data stays inside each warp
 };
 
 struct PlanPass {

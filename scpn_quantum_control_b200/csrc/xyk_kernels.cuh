@@ -340,7 +340,7 @@ struct PassDesc {
         uint8_t regpos[8];   // tile-local position of register bit k (RB used)
         uint16_t regsw[8];   // swizzled shared-memory slot offset of register bit k
         uint32_t mask;       // enabled pair slots
-        uint32_t pad;
+        uint32_t cta_sync;   // 1: block-wide barrier after this round's exchange; 0: warp-level barrier suffices
         double ca[NSLOT];    // shear form: -tan(phi/2); standard form: cos(phi)
         double cb[NSLOT];    // sin(phi)
     };
@@ -419,7 +419,6 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     }
 
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        __syncthreads();  // every warp is done reading the previous tile out of shared memory
         const double2* src = in + (t << TB);
         uint64_t obase = 0;
         for (int b = 0; b < P.nq - TB; ++b)
@@ -449,6 +448,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                         a[j] = __ldcs(p0 + off);
                     }
                 } else {
+                    __syncthreads();  // every warp is done reading the previous tile out of shared memory
 #pragma unroll
                     for (int k = 0; k < NREG; ++k) {
                         const uint32_t hi = swz<TB>((uint32_t)k << NT);  // constant after unrolling
@@ -523,6 +523,8 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     __stcs(dst + off, a[j]);
                 }
             } else {
+                // tile boundary: the previous tile's last round (other warps) must be done reading
+                if (r == 0 && (flags & kPassFuseLoad)) __syncthreads();
 #pragma unroll
                 for (int j = 0; j < NREG; ++j) {
                     uint32_t off = 0;
@@ -531,7 +533,8 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                         if ((j >> k) & 1) off ^= rb[k];
                     tile[base ^ off] = a[j];
                 }
-                __syncthreads();
+                if (R.cta_sync) __syncthreads();
+                else __syncwarp();
             }
         }
 

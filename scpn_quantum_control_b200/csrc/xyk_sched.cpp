@@ -513,6 +513,46 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         pp.fuse_load = fl;
         pp.fuse_store = fs;
 
+        // "warp qubits": the two tile qubits mapped to the warp-index bits of a round.  While
+        // they stay the same (and out of the register sets) over consecutive rounds, each warp
+        // exchanges data only with itself through shared memory and a warp-level barrier
+        // suffices; the block-wide barrier is needed only where they change.
+        const int NTB = TB - RB;                 // thread bits
+        const int nwarpbits = NTB > 5 ? NTB - 5 : 0;
+        std::vector<uint64_t> wsel(nrounds, 0);
+        std::vector<uint64_t> forced(nrounds, 0);  // qubits that must be LANE bits in that round
+        {
+            std::vector<int> inv_next(nq);
+            for (int q = 0; q < nq; ++q) inv_next[layouts[p + 1][q]] = q;
+            if (fl)
+                for (int b = 0; b < c_lane; ++b) forced[0] |= 1ull << inv[b];
+            if (fs) {
+                // lanes of the last round follow ascending output position: the 5 lowest
+                std::vector<int> cand;
+                for (int q = 0; q < nq; ++q)
+                    if (((rp.tmask >> q) & 1) && !((rr[p][nrounds - 1].rmask >> q) & 1)) cand.push_back(q);
+                std::sort(cand.begin(), cand.end(), [&](int a, int b) { return layouts[p + 1][a] < layouts[p + 1][b]; });
+                for (int k = 0; k < (int)cand.size() - nwarpbits; ++k) forced[nrounds - 1] |= 1ull << cand[k];
+            }
+            int r0 = 0;
+            while (r0 < nrounds && nwarpbits > 0) {
+                uint64_t X = rp.tmask & ~rr[p][r0].rmask & ~forced[r0];
+                int r1 = r0;
+                while (r1 + 1 < nrounds) {
+                    const uint64_t X2 = X & ~rr[p][r1 + 1].rmask & ~forced[r1 + 1];
+                    if (popc(X2) < nwarpbits) break;
+                    X = X2;
+                    ++r1;
+                }
+                // keep the highest-numbered candidates (arbitrary but deterministic)
+                uint64_t W = 0;
+                for (int q = nq - 1; q >= 0 && popc(W) < nwarpbits; --q)
+                    if ((X >> q) & 1) W |= 1ull << q;
+                for (int r = r0; r <= r1; ++r) wsel[r] = W;
+                r0 = r1 + 1;
+            }
+        }
+
         for (int r = 0; r < nrounds; ++r) {
             const RawRound& R = rr[p][r];
             PlanRound pr;
@@ -525,43 +565,51 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 pr.regq[k] = rq[k];
                 pr.regpos[k] = qpos[rq[k]];
             }
-            std::vector<int> freepos;
+            // lane positions (everything that is neither a register nor a warp qubit), warp positions
+            std::vector<int> lanepos, warppos;
             for (int pos = 0; pos < TB; ++pos) {
                 bool isreg = false;
                 for (int k = 0; k < RB; ++k) isreg |= (pr.regpos[k] == pos);
-                if (!isreg) freepos.push_back(pos);
+                if (isreg) continue;
+                if ((wsel[r] >> inv[pos]) & 1) warppos.push_back(pos);
+                else lanepos.push_back(pos);
             }
-            const int nthr = (int)freepos.size();
+            const int nl = (int)lanepos.size();
             std::vector<int> order;
             if (r == 0 && fl) {
-                order = freepos;  // ascending: lanes 0.. sit on the lowest physical bits
+                order = lanepos;  // ascending: lanes 0.. sit on the lowest physical bits
             } else if (r == nrounds - 1 && fs) {
-                order = freepos;  // ascending OUTPUT position: lanes 0.. write contiguous addresses
+                order = lanepos;  // ascending OUTPUT position: lanes 0.. write contiguous addresses
                 std::sort(order.begin(), order.end(), [&](int a, int b) { return pp.out_of_in[a] < pp.out_of_in[b]; });
             } else {
                 // three positions with linearly independent swizzle vectors first (bank-conflict free)
                 int pick[3] = {-1, -1, -1};
                 bool found = false;
-                for (int a = 0; a < nthr && !found; ++a)
-                    for (int b = a + 1; b < nthr && !found; ++b)
-                        for (int c = b + 1; c < nthr && !found; ++c) {
-                            const int va = swizzle_vec(freepos[a]), vb = swizzle_vec(freepos[b]),
-                                      vc = swizzle_vec(freepos[c]);
+                for (int a = 0; a < nl && !found; ++a)
+                    for (int b = a + 1; b < nl && !found; ++b)
+                        for (int c = b + 1; c < nl && !found; ++c) {
+                            const int va = swizzle_vec(lanepos[a]), vb = swizzle_vec(lanepos[b]),
+                                      vc = swizzle_vec(lanepos[c]);
                             if (va != vb && va != vc && vb != vc && (va ^ vb) != vc) {
                                 pick[0] = a; pick[1] = b; pick[2] = c;
                                 found = true;
                             }
                         }
-                std::vector<char> used(nthr, 0);
+                std::vector<char> used(nl, 0);
                 if (found)
                     for (int k = 0; k < 3; ++k) {
-                        order.push_back(freepos[pick[k]]);
+                        order.push_back(lanepos[pick[k]]);
                         used[pick[k]] = 1;
                     }
-                for (int a = 0; a < nthr; ++a)
-                    if (!used[a]) order.push_back(freepos[a]);
+                for (int a = 0; a < nl; ++a)
+                    if (!used[a]) order.push_back(lanepos[a]);
             }
+            for (int wpos : warppos) order.push_back(wpos);
+            const int nthr = (int)order.size();
             for (int b = 0; b < nthr; ++b) pr.thrpos[b] = order[b];
+            // barrier kind after this round's exchange
+            pr.cta_sync_after = 1;
+            if (nwarpbits > 0 && r + 1 < nrounds && wsel[r + 1] == wsel[r]) pr.cta_sync_after = 0;
             for (int c : R.cidx) {
                 const Gate& q = g[rp.gate_idx[c]];
                 int a = -1, b = -1;
@@ -644,7 +692,7 @@ std::string plan_to_json(const Plan& plan) {
             for (int k = 0; k < plan.RB; ++k) os << (k ? "," : "") << pr.regpos[k];
             os << "],\"thrpos\":[";
             for (int k = 0; k < plan.TB - plan.RB; ++k) os << (k ? "," : "") << pr.thrpos[k];
-            os << "],\"mask\":" << pr.mask << ",\"gates\":[";
+            os << "],\"mask\":" << pr.mask << ",\"cta_sync_after\":" << pr.cta_sync_after << ",\"gates\":[";
             bool firstg = true;
             int slot = 0;
             for (int a = 0; a < plan.RB; ++a)
