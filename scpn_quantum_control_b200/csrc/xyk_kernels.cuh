@@ -379,18 +379,44 @@ __device__ __forceinline__ void rotate2(double& x, double& y, double ca, double 
 // the enabled rotations among its RB register qubits and exchanges through swizzled shared
 // memory, and the last round scatters the result through the output bit permutation (straight
 // from registers when the schedule allows, else through shared memory).
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const double2& v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+
 template <int TB, int RB, bool LIFT, int MINB>
 __global__ void __launch_bounds__(1 << (TB - RB), MINB)
 tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                  const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles) {
-    constexpr int NT = TB - RB, NREG = 1 << RB;
+    constexpr int NT = TB - RB, NTHR = 1 << NT, NREG = 1 << RB;
     using Round = typename PassDesc<TB, RB>::Round;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint16_t base_tab[kMaxRounds][NTHR];  // swizzled byte offset (>>4 <<4) of each thread's base slot per round
+    const uint32_t tile_u32 = (uint32_t)__cvta_generic_to_shared(smem_raw);
     double2* tile = reinterpret_cast<double2*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t flags = P.flags;
     const int nr = P.nrounds;
 
+    // per-thread constants: shared-memory base slot of every round (tile independent)
+    for (int r = 0; r < nr; ++r) {
+        uint32_t lin = 0;
+#pragma unroll
+        for (int b = 0; b < NT; ++b)
+            if ((tid >> b) & 1u) lin |= 1u << P.rounds[r].thrpos[b];
+        base_tab[r][tid] = (uint16_t)(swz<TB>(lin) << 4);  // 2^TB * 16 B = 64 KiB: fits 16 bits
+    }
+    uint32_t lin0 = 0;  // unswizzled round-0 index (fused global load)
+#pragma unroll
+    for (int b = 0; b < NT; ++b)
+        if ((tid >> b) & 1u) lin0 |= 1u << P.rounds[0].thrpos[b];
     // per-thread constants of the (unfused) load and store phases
     const uint32_t ld_slot = swz<TB>(tid);  // index bits [0, NT) <- thread id
     uint32_t st_l = 0;
@@ -417,28 +443,29 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             ph_thr += ((tid >> b) & 1u) ? -wv : wv;
         }
     }
+    __syncthreads();  // base_tab visible (each thread only reads its own column, but keep it simple)
 
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const double2* src = in + (t << TB);
+        // pull the next tile of this CTA into L2 while this one is being processed
+        if (tid == 0 && t + gridDim.x < ntiles) prefetch_l2_bulk(in + ((t + gridDim.x) << TB), (uint32_t)(sizeof(double2) << TB));
         uint64_t obase = 0;
         for (int b = 0; b < P.nq - TB; ++b)
             if ((t >> b) & 1ull) obase |= 1ull << P.hi_out[b];
+        uint32_t base_next = base_tab[0][tid];
 
         for (int r = 0; r < nr; ++r) {
             const Round& R = P.rounds[r];
-            uint32_t lin = 0;
-#pragma unroll
-            for (int b = 0; b < NT; ++b)
-                if ((tid >> b) & 1u) lin |= 1u << R.thrpos[b];
-            const uint32_t base = swz<TB>(lin);
+            const uint32_t boff = base_next;                    // byte offset of this thread's base slot in the tile
+            if (r + 1 < nr) base_next = base_tab[r + 1][tid];   // off the critical path of the next round
             uint32_t rb[RB];
 #pragma unroll
-            for (int k = 0; k < RB; ++k) rb[k] = R.regsw[k];
+            for (int k = 0; k < RB; ++k) rb[k] = (uint32_t)R.regsw[k] << 4;
             double2 a[NREG];
 
             if (r == 0) {
                 if (flags & kPassFuseLoad) {
-                    const double2* p0 = src + lin;
+                    const double2* p0 = src + lin0;
 #pragma unroll
                     for (int j = 0; j < NREG; ++j) {
                         uint32_t off = 0;
@@ -462,7 +489,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
                         for (int k = 0; k < RB; ++k)
                             if ((j >> k) & 1) off ^= rb[k];
-                        a[j] = tile[base ^ off];
+                        a[j] = lds128(tile_u32 + (boff ^ off));
                     }
                 }
                 if (flags & kPassHasPhase) {
@@ -489,7 +516,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
                     for (int k = 0; k < RB; ++k)
                         if ((j >> k) & 1) off ^= rb[k];
-                    a[j] = tile[base ^ off];
+                    a[j] = lds128(tile_u32 + (boff ^ off));
                 }
             }
 
@@ -531,7 +558,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
                     for (int k = 0; k < RB; ++k)
                         if ((j >> k) & 1) off ^= rb[k];
-                    tile[base ^ off] = a[j];
+                    sts128(tile_u32 + (boff ^ off), a[j]);
                 }
                 if (R.cta_sync) __syncthreads();
                 else __syncwarp();
