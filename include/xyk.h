@@ -90,6 +90,10 @@ int xyk_continue(xyk_handle h);
  * in world_size equal contiguous blocks (block s goes to / comes from rank s). */
 int xyk_exchange_info(xyk_handle h, void **src, void **dst, size_t *bytes_per_block);
 int xyk_exchange_done(xyk_handle h);
+/* Request an exchange outside apply_layers (observables on sharded qubits, canonical layouts):
+ * the g = log2(world_size) logical qubits outgoing[0..g) leave, the sharded ones arrive.
+ * Returns XYK_NEED_EXCHANGE; the host then proceeds as above. */
+int xyk_begin_exchange(xyk_handle h, const int *outgoing);
 
 /* <X_q>, <Y_q> for every qubit (partial sums over this shard for sharded handles: the host
  * adds the per-rank arrays).  Qubits that are currently global on a sharded handle are

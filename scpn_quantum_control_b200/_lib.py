@@ -61,6 +61,7 @@ PROTOTYPES = {
     "xyk_continue": (c_int, [c_void_p]),
     "xyk_exchange_info": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t)]),
     "xyk_exchange_done": (c_int, [c_void_p]),
+    "xyk_begin_exchange": (c_int, [c_void_p, POINTER(c_int)]),
     "xyk_xy_expectations": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "xyk_order_parameter": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "xyk_z_expectations": (c_int, [c_void_p, POINTER(c_double)]),

@@ -30,8 +30,15 @@ thread_local std::string g_global_error;
 
 struct Program {
     Plan plan;
+    std::vector<int> loc2log;       // logical qubit of plan index l (identity on a single GPU)
     std::vector<Desc> descs;        // one per pass
     std::vector<char> lift;         // shear form allowed for the pass
+};
+
+struct ShardStep {
+    bool is_exchange = false;
+    std::shared_ptr<Program> prog;
+    std::vector<int> outgoing, incoming;
 };
 
 }  // namespace
@@ -51,6 +58,7 @@ struct xyk_handle_s {
     int engine_opt = XYK_ENGINE_AUTO;
     int fuse_phase = 1;
     int tiled_obs = 1;
+    int debug_mode = 0;  // timing experiments only (results are wrong): 1 = no gates, 2 = one empty round per pass
     int sm_count = 148;
     int pass_grid = 0;
     // scratch
@@ -62,6 +70,12 @@ struct xyk_handle_s {
     xyk_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> pass_events;  // per-launch timing of the tile pass kernel
+    // sharded execution state machine
+    std::vector<ShardStep> shard_steps;
+    size_t shard_pos = 0;
+    bool exchange_pending = false;
+    std::vector<int> ex_out, ex_in;
+    int64_t exchanges = 0;
     std::string err;
 };
 
@@ -228,8 +242,8 @@ int relayout(xyk_handle h, const std::vector<int>& target) {
     return XYK_OK;
 }
 
-void fill_desc(xyk_handle h, const Plan& plan, const PlanPass& pp, const std::vector<int>& perm_in, Desc& d,
-               bool& lift_ok) {
+void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, const PlanPass& pp,
+               const std::vector<int>& perm_in, Desc& d, bool& lift_ok) {
     std::memset(&d, 0, sizeof(d));
     d.nq = plan.nq;
     d.nrounds = (int)pp.rounds.size();
@@ -250,15 +264,29 @@ void fill_desc(xyk_handle h, const Plan& plan, const PlanPass& pp, const std::ve
     if (pp.has_phase && h->fuse_phase && !h->zterms.empty()) {
         d.flags |= kPassHasPhase;
         d.ph_tau = pp.ztau;
-        std::vector<double> wq(plan.nq, 0.0);
-        for (const auto& z : h->zterms) wq[z.i] = z.w;
-        for (int q = 0; q < plan.nq; ++q) d.ph_w[perm_in[q]] = wq[q];
+        std::vector<double> wlog(h->n, 0.0);
+        for (const auto& z : h->zterms) wlog[z.i] = z.w;
+        std::vector<char> is_local(h->n, 0);
+        for (int l = 0; l < plan.nq; ++l) {
+            d.ph_w[perm_in[l]] = wlog[loc2log[l]];
+            is_local[loc2log[l]] = 1;
+        }
+        // sharded qubits: their bit is fixed by the rank (the caller guarantees h->perm is current for them)
+        double pc = 0.0;
+        for (int q = 0; q < h->n; ++q)
+            if (!is_local[q]) pc += wlog[q] * (((h->rank >> (h->perm[q] - h->nlocal)) & 1) ? -1.0 : 1.0);
+        d.ph_const = pc;
         const PlanRound& r0 = pp.rounds.front();
         for (int j = 0; j < (1 << kRB); ++j) {
             double ph = 0.0;
             for (int k = 0; k < kRB; ++k) ph += d.ph_w[r0.regpos[k]] * (((j >> k) & 1) ? -1.0 : 1.0);
             d.ph_reg[j] = make_double2(std::cos(pp.ztau * ph), std::sin(pp.ztau * ph));
         }
+    }
+    if (h->debug_mode == 2) {  // timing experiment: pure permuting copy through round 0 only
+        d.nrounds = 1;
+        for (int b = 0; b < Desc::NT; ++b) d.last_thr_out[b] = (uint8_t)pp.out_of_in[pp.rounds[0].thrpos[b]];
+        for (int k = 0; k < kRB; ++k) d.last_reg_out[k] = (uint8_t)pp.out_of_in[pp.rounds[0].regpos[k]];
     }
     lift_ok = true;
     for (int r = 0; r < d.nrounds; ++r) {
@@ -280,7 +308,7 @@ void fill_desc(xyk_handle h, const Plan& plan, const PlanPass& pp, const std::ve
             if (pr.regpos[k] >= 3) sw ^= (uint32_t)swizzle_vec(pr.regpos[k]);
             R.regsw[k] = (uint16_t)sw;
         }
-        R.mask = pr.mask;
+        R.mask = h->debug_mode ? 0u : pr.mask;
         R.cta_sync = (uint32_t)pr.cta_sync_after;
         for (int s = 0; s < Desc::NSLOT; ++s) {
             if (!((pr.mask >> s) & 1u)) continue;
@@ -296,6 +324,20 @@ void fill_desc(xyk_handle h, const Plan& plan, const PlanPass& pp, const std::ve
     }
 }
 
+void finish_program(xyk_handle h, Program& prog) {
+    prog.descs.resize(prog.plan.passes.size());
+    prog.lift.resize(prog.plan.passes.size());
+    std::vector<int> perm(prog.plan.start_perm);
+    for (size_t p = 0; p < prog.plan.passes.size(); ++p) {
+        bool lift = true;
+        fill_desc(h, prog.plan, prog.loc2log, prog.plan.passes[p], perm, prog.descs[p], lift);
+        prog.lift[p] = lift ? 1 : 0;
+        std::vector<int> np(perm);
+        for (int q = 0; q < prog.plan.nq; ++q) np[q] = prog.plan.passes[p].out_of_in[perm[q]];
+        perm.swap(np);
+    }
+}
+
 std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int reps) {
     const auto key = std::make_tuple(h->problem_version * 2 + (uint64_t)(h->fuse_phase ? 1 : 0), order, reps, delta);
     auto it = h->programs.find(key);
@@ -307,20 +349,11 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
     cfg.TB = kTB;
     cfg.RB = kRB;
     cfg.max_rounds = kMaxRounds;
-    // only local qubits can be scheduled here (single-GPU: all of them)
     prog->plan = compile_plan(h->nlocal, segs, cfg);
     prog->plan.layers1_equiv = l1;
-    prog->descs.resize(prog->plan.passes.size());
-    prog->lift.resize(prog->plan.passes.size());
-    std::vector<int> perm(prog->plan.start_perm);
-    for (size_t p = 0; p < prog->plan.passes.size(); ++p) {
-        bool lift = true;
-        fill_desc(h, prog->plan, prog->plan.passes[p], perm, prog->descs[p], lift);
-        prog->lift[p] = lift ? 1 : 0;
-        std::vector<int> np(perm);
-        for (int q = 0; q < prog->plan.nq; ++q) np[q] = prog->plan.passes[p].out_of_in[perm[q]];
-        perm.swap(np);
-    }
+    prog->loc2log.resize(h->nlocal);
+    for (int l = 0; l < h->nlocal; ++l) prog->loc2log[l] = l;
+    finish_program(h, *prog);
     if (h->programs.size() > 64) h->programs.clear();
     h->programs[key] = prog;
     return prog;
@@ -345,9 +378,9 @@ int run_program_tiled(xyk_handle h, Program& prog) {
         rc = configure_pass_kernels(h);
         if (rc) return rc;
     }
-    if (!plan.passes.empty()) {
+    {
         std::vector<int> target(h->perm);
-        for (int q = 0; q < plan.nq; ++q) target[q] = plan.start_perm[q];
+        for (int l = 0; l < plan.nq; ++l) target[prog.loc2log[l]] = plan.start_perm[l];
         rc = relayout(h, target);
         if (rc) return rc;
     }
@@ -378,7 +411,7 @@ int run_program_tiled(xyk_handle h, Program& prog) {
         if (h->stats.timing_enabled) cudaEventRecord(h->pass_events[2 * p + 1], h->stream);
         h->cur ^= 1;
         std::vector<int> np(h->perm);
-        for (int q = 0; q < plan.nq; ++q) np[q] = pp.out_of_in[h->perm[q]];
+        for (int l = 0; l < plan.nq; ++l) np[prog.loc2log[l]] = pp.out_of_in[h->perm[prog.loc2log[l]]];
         h->perm.swap(np);
         h->stats.kernel_launches++;
         h->stats.pass_launches++;
@@ -421,8 +454,11 @@ int xy_expect_device(xyk_handle h) {
     const int grid = std::min(kRedBlocks, grid_for(h, half, 256));
     for (int q = 0; q < h->n; ++q) {
         const int pos = h->perm[q];
-        XYK_CHECK(h, pos < h->nlocal, XYK_ERR_UNSUPPORTED, "observable on a sharded qubit needs an exchange first");
         double2* part = (double2*)h->d_partial + (size_t)q * kRedBlocks;
+        if (pos >= h->nlocal) {  // sharded qubit: reported as 0 here, the host measures it after an exchange
+            cudaMemsetAsync(part, 0, sizeof(double2) * grid, h->stream);
+            continue;
+        }
         if (h->dtype == 0)
             xy_expect_kernel<double><<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], h->nlocal, pos, part);
         else
@@ -432,6 +468,102 @@ int xy_expect_device(xyk_handle h) {
     xy_finalize_kernel<<<h->n, 128, 0, h->stream>>>((const double2*)h->d_partial, grid, kRedBlocks, h->d_out);
     h->stats.kernel_launches++;
     XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
+// logical qubits currently sharded: rank bit k carries global_qubits[k]
+std::vector<int> current_globals(xyk_handle h) {
+    std::vector<int> g(h->gbits, -1);
+    for (int q = 0; q < h->n; ++q)
+        if (h->perm[q] >= h->nlocal) g[h->perm[q] - h->nlocal] = q;
+    return g;
+}
+
+// place `outgoing[k]` on local physical bit nlocal - g + k (everything else keeps its relative order)
+int stage_outgoing(xyk_handle h, const std::vector<int>& outgoing) {
+    std::vector<int> target(h->perm);
+    std::vector<char> is_out(h->n, 0);
+    for (int q : outgoing) is_out[q] = 1;
+    std::vector<std::pair<int, int>> locals;  // (current position, qubit)
+    for (int q = 0; q < h->n; ++q)
+        if (h->perm[q] < h->nlocal && !is_out[q]) locals.push_back({h->perm[q], q});
+    std::sort(locals.begin(), locals.end());
+    int pos = 0;
+    for (auto& pq : locals) target[pq.second] = pos++;
+    for (int q : outgoing) target[q] = pos++;
+    return relayout(h, target);
+}
+
+int run_shard_steps(xyk_handle h) {
+    while (h->shard_pos < h->shard_steps.size()) {
+        ShardStep& st = h->shard_steps[h->shard_pos];
+        if (!st.is_exchange) {
+            int rc = run_program_tiled(h, *st.prog);
+            if (rc) return rc;
+            h->shard_pos++;
+            continue;
+        }
+        for (int q : st.outgoing)
+            XYK_CHECK(h, h->perm[q] < h->nlocal, XYK_ERR_STATE, "exchange: outgoing qubit is not local");
+        int rc = stage_outgoing(h, st.outgoing);
+        if (rc) return rc;
+        rc = ensure_alt(h);
+        if (rc) return rc;
+        h->ex_out = st.outgoing;
+        h->ex_in = current_globals(h);
+        h->exchange_pending = true;
+        XYK_CUDA(h, cudaStreamSynchronize(h->stream));  // the host's collective runs on another stream
+        return XYK_NEED_EXCHANGE;
+    }
+    h->shard_steps.clear();
+    h->shard_pos = 0;
+    return XYK_OK;
+}
+
+int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1) {
+    SchedConfig cfg;
+    cfg.TB = kTB;
+    cfg.RB = kRB;
+    cfg.max_rounds = kMaxRounds;
+    std::vector<ShardOp> ops;
+    try {
+        ops = compile_sharded(h->n, current_globals(h), segs, cfg, nullptr);
+    } catch (const std::exception& e) {
+        return fail(h, XYK_ERR_INVALID, e.what());
+    }
+    h->shard_steps.clear();
+    h->shard_pos = 0;
+    // perm of the sharded qubits evolves with the exchanges: descriptors need the rank-bit position of
+    // every global qubit at the time the pass runs, so track it while building
+    std::vector<int> saved_perm(h->perm);
+    int gates = 0, rounds = 0, passes = 0;
+    for (auto& op : ops) {
+        ShardStep st;
+        st.is_exchange = op.is_exchange;
+        if (op.is_exchange) {
+            st.outgoing = op.outgoing;
+            st.incoming = op.incoming;
+            for (int k = 0; k < h->gbits; ++k) {
+                h->perm[op.outgoing[k]] = h->nlocal + k;                 // leaves to rank bit k
+                h->perm[op.incoming[k]] = h->nlocal - h->gbits + k;      // arrives on the top local bits
+            }
+        } else {
+            st.prog = std::make_shared<Program>();
+            st.prog->plan = std::move(op.plan);
+            st.prog->plan.layers1_equiv = 0;
+            st.prog->loc2log = op.loc2log;
+            finish_program(h, *st.prog);
+            gates += st.prog->plan.total_gates;
+            rounds += st.prog->plan.total_rounds;
+            passes += (int)st.prog->plan.passes.size();
+        }
+        h->shard_steps.push_back(std::move(st));
+    }
+    h->perm = saved_perm;
+    h->stats.last_gates = gates;
+    h->stats.last_rounds = rounds;
+    h->stats.last_passes = passes;
+    h->stats.last_layers1 = l1;
     return XYK_OK;
 }
 
@@ -544,6 +676,10 @@ int xyk_set_option(xyk_handle h, int option, int64_t value) {
         case XYK_OPT_TILED_OBS:
             h->tiled_obs = value != 0;
             return XYK_OK;
+        case 100:
+            h->debug_mode = (int)value;
+            h->programs.clear();
+            return XYK_OK;
         default:
             return fail(h, XYK_ERR_INVALID, "unknown option");
     }
@@ -588,8 +724,17 @@ int xyk_apply_layers(xyk_handle h, double delta, int order, int reps) {
     XYK_CHECK(h, order == 1 || order == 2 || order == 4 || order == 6, XYK_ERR_INVALID, "order must be 1, 2, 4 or 6");
     XYK_CHECK(h, reps >= 1, XYK_ERR_INVALID, "reps must be >= 1");
     XYK_CHECK(h, std::isfinite(delta), XYK_ERR_INVALID, "delta must be finite");
-    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "sharded evolution is driven through xyk_continue (not in this build)");
     XYK_CUDA(h, cudaSetDevice(h->device));
+    if (h->world > 1) {
+        XYK_CHECK(h, h->dtype == 0 && h->nlocal >= kTB, XYK_ERR_UNSUPPORTED,
+                  "sharded evolution needs complex128 and at least 12 local qubits");
+        XYK_CHECK(h, !h->exchange_pending && h->shard_steps.empty(), XYK_ERR_STATE, "a sharded call is still in flight");
+        int l1s = 0;
+        std::vector<Segment> ssegs = build_sequence(h->pairs, delta, order, reps, &l1s);
+        int rcs = build_shard_steps(h, ssegs, l1s);
+        if (rcs) return rcs;
+        return run_shard_steps(h);
+    }
     if (use_tiled(h)) {
         std::shared_ptr<Program> prog;
         try {
@@ -611,9 +756,50 @@ int xyk_apply_layers(xyk_handle h, double delta, int order, int reps) {
     return rc;
 }
 
-int xyk_continue(xyk_handle h) { return fail(h, XYK_ERR_UNSUPPORTED, "not a sharded handle"); }
-int xyk_exchange_info(xyk_handle h, void**, void**, size_t*) { return fail(h, XYK_ERR_UNSUPPORTED, "not a sharded handle"); }
-int xyk_exchange_done(xyk_handle h) { return fail(h, XYK_ERR_UNSUPPORTED, "not a sharded handle"); }
+int xyk_continue(xyk_handle h) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->world > 1, XYK_ERR_UNSUPPORTED, "not a sharded handle");
+    XYK_CHECK(h, !h->exchange_pending, XYK_ERR_STATE, "an exchange is pending: call xyk_exchange_done first");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    return run_shard_steps(h);
+}
+
+int xyk_exchange_info(xyk_handle h, void** src, void** dst, size_t* bytes_per_block) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->exchange_pending, XYK_ERR_STATE, "no exchange pending");
+    if (src) *src = h->buf[h->cur];
+    if (dst) *dst = h->buf[h->cur ^ 1];
+    if (bytes_per_block) *bytes_per_block = h->bytes / (size_t)h->world;
+    return XYK_OK;
+}
+
+int xyk_exchange_done(xyk_handle h) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->exchange_pending, XYK_ERR_STATE, "no exchange pending");
+    h->cur ^= 1;
+    for (int k = 0; k < h->gbits; ++k) {
+        h->perm[h->ex_out[k]] = h->nlocal + k;
+        h->perm[h->ex_in[k]] = h->nlocal - h->gbits + k;
+    }
+    h->exchange_pending = false;
+    h->exchanges++;
+    h->stats.state_sweeps++;
+    if (h->shard_pos < h->shard_steps.size() && h->shard_steps[h->shard_pos].is_exchange) h->shard_pos++;
+    return XYK_OK;
+}
+
+int xyk_begin_exchange(xyk_handle h, const int* outgoing) {
+    if (!h || !outgoing) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->world > 1, XYK_ERR_UNSUPPORTED, "not a sharded handle");
+    XYK_CHECK(h, !h->exchange_pending && h->shard_steps.empty(), XYK_ERR_STATE, "a sharded call is still in flight");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    ShardStep st;
+    st.is_exchange = true;
+    st.outgoing.assign(outgoing, outgoing + h->gbits);
+    h->shard_steps.push_back(st);
+    h->shard_pos = 0;
+    return run_shard_steps(h);
+}
 
 int xyk_xy_expectations(xyk_handle h, double* exp_x, double* exp_y) {
     if (!h || !exp_x || !exp_y) return XYK_ERR_INVALID;
@@ -761,7 +947,11 @@ int xyk_get_state(xyk_handle h, void* dst, int is_device) {
     XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
     XYK_CUDA(h, cudaSetDevice(h->device));
     const void* src = h->buf[h->cur];
-    if (!perm_is_identity(h)) {
+    if (h->world > 1) {
+        int rcc = xyk_canonicalise(h);
+        if (rcc) return rcc;
+        src = h->buf[h->cur];
+    } else if (!perm_is_identity(h)) {
         // canonical copy into the spare buffer; the live state keeps its layout
         PermSpec S{};
         S.nlocal = h->nlocal;
@@ -816,8 +1006,14 @@ int xyk_canonicalise(xyk_handle h) {
     if (!h) return XYK_ERR_INVALID;
     XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
     XYK_CUDA(h, cudaSetDevice(h->device));
-    std::vector<int> target(h->n);
-    for (int q = 0; q < h->n; ++q) target[q] = q;
+    std::vector<int> target(h->perm);
+    if (h->world == 1) {
+        for (int q = 0; q < h->n; ++q) target[q] = q;
+    } else {  // local qubits in ascending order on the local bits; sharded qubits stay where they are
+        int pos = 0;
+        for (int q = 0; q < h->n; ++q)
+            if (h->perm[q] < h->nlocal) target[q] = pos++;
+    }
     return relayout(h, target);
 }
 

@@ -82,6 +82,8 @@ struct SchedConfig {
     int max_rounds = 14;   // rounds a single pass descriptor can carry
     int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
+    bool cyclic = true;    // the program ends in its own start layout (it can be replayed back to back)
+    std::vector<int> final_top;  // non-cyclic: qubits that must end on the highest physical bits, in this order
 };
 
 // Compile the segments into tile passes over nq local qubits.  Throws std::runtime_error.
@@ -94,5 +96,24 @@ inline int swizzle_vec(int p) {
 }
 
 std::string plan_to_json(const Plan& plan);
+
+// ---- sharded state (top g physical bits = rank): local programs separated by exchanges ----
+struct ShardOp {
+    bool is_exchange = false;
+    // local program
+    std::vector<int> loc2log;   // logical qubit of local index l (ascending)
+    Plan plan;                  // over local indices
+    // exchange: the g qubits on the top local physical bits swap with the g global qubits
+    std::vector<int> outgoing;  // logical qubits leaving (to be placed on the top local bits, in this order)
+    std::vector<int> incoming;  // logical qubits arriving (currently on rank bit k, in this order)
+};
+
+// Greedy schedule for a state whose `global_qubits` (logical ids, rank bit k -> global_qubits[k])
+// are sharded across 2^g ranks: run every gate whose qubits are both local (dependency closure),
+// then exchange the g global qubits with the g local qubits whose next use lies furthest ahead.
+std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubits, const std::vector<Segment>& segs,
+                                     const SchedConfig& cfg, std::vector<int>* global_final);
+
+std::string sharded_to_json(const std::vector<ShardOp>& ops);
 
 }  // namespace xyk

@@ -353,6 +353,7 @@ struct PassDesc {
     uint8_t st_odst[16];     //                that output bit
     uint8_t last_thr_out[8]; // fused store: output bit of the qubit on thread bit b of the LAST round
     uint8_t last_reg_out[8]; //              output bit of the qubit on register bit k of the LAST round
+    double ph_const;         // fused phase: contribution of the sharded (rank) bits, constant on this device
     double ph_tau;           // fused phase: exp(+i tau sum_b w_b (1 - 2 bit_b)) over all input bits
     double ph_w[kMaxQ];      // omega of the logical qubit on INPUT physical bit b
     double2 ph_reg[1 << RB]; // phase factor of register index j in round 0
@@ -435,7 +436,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
         st_l = swz<TB>(st_l);
     }
     // fused phase: contribution of this thread's round-0 index bits
-    double ph_thr = 0.0;
+    double ph_thr = P.ph_const;
     if (flags & kPassHasPhase) {
 #pragma unroll
         for (int b = 0; b < NT; ++b) {

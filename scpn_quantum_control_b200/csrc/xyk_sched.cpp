@@ -279,7 +279,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // cyclic closure: the last tile must share `need` qubits with the first one so that the
     // program can be replayed from its own end layout.  If it does not, peel gates off the last
     // pass(es) and re-plan them with the extra constraint.
-    if (!raw.empty() && popc(raw.back().tmask & first_tile) < need && nq > TB) {
+    if (cfg.cyclic && !raw.empty() && popc(raw.back().tmask & first_tile) < need && nq > TB) {
         const int s = raw.back().seg;
         const std::vector<Gate>& g = sg[s];
         // undo the last pass of segment s and re-plan the remaining gates of s
@@ -317,6 +317,15 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // layout between the two passes, which lets the last round store and the next first round
     // load global memory directly with lanes on contiguous addresses.
     const int P = (int)raw.size();
+    auto next_tile = [&](int p) -> uint64_t {
+        if (P == 1 && cfg.cyclic) return 0;
+        if (p + 1 < P) return raw[p + 1].tmask;
+        return cfg.cyclic ? raw[0].tmask : 0;
+    };
+    auto prev_index = [&](int p) -> int {
+        if (p > 0) return p - 1;
+        return (cfg.cyclic && P > 1) ? P - 1 : -1;
+    };
     struct RawRound {
         uint64_t rmask = 0;
         std::vector<int> cidx;  // indices into the pass's gate_idx
@@ -391,7 +400,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     for (int p = 0; p < P; ++p) {
         const RawPass& rp = raw[p];
         const std::vector<Gate>& g = sg[rp.seg];
-        const uint64_t shared_next = P == 1 ? 0 : (rp.tmask & raw[(p + 1) % P].tmask);
+        const uint64_t shared_next = rp.tmask & next_tile(p);
         const int s = popc(shared_next);
         RawRound best;
         if (cfg.fuse_io && s - c_lane >= 1) {
@@ -414,12 +423,13 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             rfirst[p] = rlast[p];
             continue;
         }
-        const int pm = (p + P - 1) % P;
-        const uint64_t shared_prev = P == 1 ? 0 : (rp.tmask & raw[pm].tmask);
-        const int budget = popc(shared_prev) - c_lane - popc(rlast[pm] & shared_prev);
+        const int pm = prev_index(p);
+        const uint64_t shared_prev = pm < 0 ? 0 : (rp.tmask & raw[pm].tmask);
+        const uint64_t rl_prev = pm < 0 ? 0 : rlast[pm];
+        const int budget = popc(shared_prev) - c_lane - popc(rl_prev & shared_prev);
         RawRound best;
-        if (cfg.fuse_io && budget >= 0) search_round(rp, g, cdone[p], false, shared_prev, budget, rlast[pm], best);
-        if (best.cidx.empty()) search_round(rp, g, cdone[p], false, 0, 99, rlast[pm], best);
+        if (cfg.fuse_io && pm >= 0 && budget >= 0) search_round(rp, g, cdone[p], false, shared_prev, budget, rl_prev, best);
+        if (best.cidx.empty()) search_round(rp, g, cdone[p], false, 0, 99, rl_prev, best);
         if (best.cidx.empty()) throw std::runtime_error("compile_plan: first-round search made no progress");
         for (int c : best.cidx) cdone[p][c] = 1;
         ndone += best.cidx.size();
@@ -443,16 +453,18 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // qubits, then the remaining tile qubits, then everything else; ascending inside each class.
     auto make_layout = [&](int p, std::vector<int>& perm, int& nshared, int& nfree) {
         const uint64_t tile = raw[p].tmask;
-        const int pm = (p + P - 1) % P;
-        const uint64_t prev = P == 1 ? 0 : raw[pm].tmask;
+        const int pm = prev_index(p);
+        const uint64_t prev = pm < 0 ? 0 : raw[pm].tmask;
+        const uint64_t rl_prev = pm < 0 ? 0 : rlast[pm];
         perm.assign(nq, -1);
         int pos = 0;
         const uint64_t shared = tile & prev;
-        const uint64_t avoid = P == 1 ? 0 : (rlast[pm] | rfirst[p]);
+        const uint64_t avoid = rl_prev | rfirst[p];
         nshared = popc(shared);
         nfree = popc(shared & ~avoid);
-        const uint64_t classes[5] = {shared & ~avoid, shared & rlast[pm] & ~rfirst[p], shared & rfirst[p] & ~rlast[pm],
-                                     shared & rfirst[p] & rlast[pm], tile & ~shared};
+        const uint64_t rest = tile & ~shared;
+        const uint64_t classes[6] = {shared & ~avoid, shared & rl_prev & ~rfirst[p], shared & rfirst[p] & ~rl_prev,
+                                     shared & rfirst[p] & rl_prev, rest & ~rfirst[p], rest & rfirst[p]};
         for (uint64_t cls : classes)
             for (int q = 0; q < nq; ++q)
                 if ((cls >> q) & 1) perm[q] = pos++;
@@ -462,15 +474,43 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     std::vector<std::vector<int>> layouts(P + 1);
     std::vector<int> nshared(P + 1, 0), nfree(P + 1, 0);
     for (int p = 0; p < P; ++p) make_layout(p, layouts[p], nshared[p], nfree[p]);
-    if (P > 0) {
+    if (P > 0 && cfg.cyclic) {
         layouts[P] = layouts[0];
         nshared[P] = nshared[0];
         nfree[P] = nfree[0];
         plan.start_perm = layouts[0];
         plan.end_perm = layouts[0];
+    } else if (P > 0) {
+        // open program: the last pass keeps its tile qubits low (those its last round does not hold in
+        // registers first, so that the store stays coalesced) and parks `final_top` on the highest bits
+        uint64_t top = 0;
+        for (int q : cfg.final_top) top |= 1ull << q;
+        const uint64_t tile = raw[P - 1].tmask & ~top;
+        std::vector<int>& perm = layouts[P];
+        perm.assign(nq, -1);
+        int pos = 0;
+        const uint64_t classes[2] = {tile & ~rlast[P - 1], tile & rlast[P - 1]};
+        for (uint64_t cls : classes)
+            for (int q = 0; q < nq; ++q)
+                if ((cls >> q) & 1) perm[q] = pos++;
+        for (int q = 0; q < nq; ++q)
+            if (!((tile >> q) & 1) && !((top >> q) & 1)) perm[q] = pos++;
+        for (int q : cfg.final_top) perm[q] = pos++;
+        nshared[P] = popc(tile);
+        nfree[P] = popc(tile & ~rlast[P - 1]);
+        plan.start_perm = layouts[0];
+        plan.end_perm = layouts[P];
     } else {
         plan.start_perm.resize(nq);
         for (int q = 0; q < nq; ++q) plan.start_perm[q] = q;
+        if (!cfg.cyclic && !cfg.final_top.empty()) {
+            uint64_t top = 0;
+            for (int q : cfg.final_top) top |= 1ull << q;
+            int pos = 0;
+            for (int q = 0; q < nq; ++q)
+                if (!((top >> q) & 1)) plan.start_perm[q] = pos++;
+            for (int q : cfg.final_top) plan.start_perm[q] = pos++;
+        }
         plan.end_perm = plan.start_perm;
     }
 
@@ -491,7 +531,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         }
         for (int b = 0; b < kMaxQ; ++b) pp.out_of_in[b] = b;
         for (int b = 0; b < nq; ++b) pp.out_of_in[b] = layouts[p + 1][inv[b]];
-        pp.n_shared = P == 1 ? TB : nshared[p + 1];
+        pp.n_shared = (P == 1 && cfg.cyclic) ? TB : nshared[p + 1];
         pp.has_phase = rp.has_phase && zeff[rp.seg] != 0.0;
         pp.ztau = pp.has_phase ? zeff[rp.seg] : 0.0;
         pp.std_rot = false;
@@ -664,6 +704,124 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         plan.passes.swap(out);
     }
     return plan;
+}
+
+std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubits, const std::vector<Segment>& segs,
+                                     const SchedConfig& cfg_in, std::vector<int>* global_final) {
+    const int g = (int)global_qubits.size();
+    const int nl = n - g;
+    if (nl < 1) throw std::runtime_error("compile_sharded: no local qubits");
+    std::vector<int> glob(global_qubits);
+    std::vector<ShardOp> ops;
+    // flattened sequence for next-use look-ahead
+    struct FG { int i, j, seg, idx; };
+    std::vector<FG> flat;
+    for (size_t s = 0; s < segs.size(); ++s)
+        for (size_t k = 0; k < segs[s].gates.size(); ++k) flat.push_back({segs[s].gates[k].i, segs[s].gates[k].j, (int)s, (int)k});
+    std::vector<char> fdone(flat.size(), 0);
+    size_t fpos = 0;  // first flat index of the current segment
+
+    for (size_t s = 0; s < segs.size(); ++s) {
+        const std::vector<GateOp>& gs = segs[s].gates;
+        std::vector<char> done(gs.size(), 0);
+        size_t ndone = 0;
+        bool first = true;
+        while (true) {
+            uint64_t gmask = 0;
+            for (int q : glob) gmask |= 1ull << q;
+            std::vector<int> loc2log;
+            for (int q = 0; q < n; ++q)
+                if (!((gmask >> q) & 1)) loc2log.push_back(q);
+            std::vector<int> log2loc(n, -1);
+            for (int l = 0; l < nl; ++l) log2loc[loc2log[l]] = l;
+            // closure of the pending gates of this segment over the local qubits
+            Segment sub;
+            sub.ztau = first ? segs[s].ztau : 0.0;
+            std::vector<int> taken;
+            {
+                uint64_t blocked = 0;
+                for (size_t k = 0; k < gs.size(); ++k) {
+                    if (done[k]) continue;
+                    const uint64_t m = (1ull << gs[k].i) | (1ull << gs[k].j);
+                    if (!(m & gmask) && !(m & blocked)) taken.push_back((int)k);
+                    else blocked |= m;
+                }
+            }
+            for (int k : taken) {
+                GateOp go = gs[k];
+                go.i = log2loc[gs[k].i];
+                go.j = log2loc[gs[k].j];
+                sub.gates.push_back(go);
+                done[k] = 1;
+                fdone[fpos + k] = 1;
+            }
+            ndone += taken.size();
+            const bool seg_finished = ndone == gs.size();
+            // which qubits leave at the next exchange (if any): furthest next use over the whole sequence
+            std::vector<int> outgoing;
+            if (!seg_finished) {
+                std::vector<size_t> next_use(n, flat.size() + 1);
+                for (size_t f = flat.size(); f-- > 0;)
+                    if (!fdone[f]) {
+                        next_use[flat[f].i] = f;
+                        next_use[flat[f].j] = f;
+                    }
+                std::vector<int> cand(loc2log);
+                std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
+                    if (next_use[a] != next_use[b]) return next_use[a] > next_use[b];
+                    return a > b;
+                });
+                outgoing.assign(cand.begin(), cand.begin() + g);
+                std::sort(outgoing.begin(), outgoing.end());
+            }
+            if (!sub.gates.empty() || (first && sub.ztau != 0.0)) {
+                ShardOp op;
+                op.loc2log = loc2log;
+                SchedConfig cfg = cfg_in;
+                cfg.cyclic = false;
+                cfg.final_top.clear();
+                for (int q : outgoing) cfg.final_top.push_back(log2loc[q]);
+                std::vector<Segment> one{sub};
+                op.plan = compile_plan(nl, one, cfg);
+                ops.push_back(std::move(op));
+                first = false;
+            }
+            if (seg_finished) break;
+            ShardOp ex;
+            ex.is_exchange = true;
+            ex.outgoing = outgoing;
+            ex.incoming = glob;
+            ops.push_back(ex);
+            glob = outgoing;  // rank bit k now carries outgoing[k]
+        }
+        fpos += gs.size();
+    }
+    if (global_final) *global_final = glob;
+    return ops;
+}
+
+std::string sharded_to_json(const std::vector<ShardOp>& ops) {
+    std::ostringstream os;
+    os << "{\"ops\":[";
+    for (size_t k = 0; k < ops.size(); ++k) {
+        const ShardOp& op = ops[k];
+        os << (k ? "," : "");
+        if (op.is_exchange) {
+            os << "{\"kind\":\"exchange\",\"outgoing\":[";
+            for (size_t i = 0; i < op.outgoing.size(); ++i) os << (i ? "," : "") << op.outgoing[i];
+            os << "],\"incoming\":[";
+            for (size_t i = 0; i < op.incoming.size(); ++i) os << (i ? "," : "") << op.incoming[i];
+            os << "]}";
+        } else {
+            os << "{\"kind\":\"local\",\"loc2log\":[";
+            for (size_t i = 0; i < op.loc2log.size(); ++i) os << (i ? "," : "") << op.loc2log[i];
+            os << "],\"end_perm\":[";
+            for (size_t i = 0; i < op.plan.end_perm.size(); ++i) os << (i ? "," : "") << op.plan.end_perm[i];
+            os << "],\"plan\":" << plan_to_json(op.plan) << "}";
+        }
+    }
+    os << "]}";
+    return os.str();
 }
 
 std::string plan_to_json(const Plan& plan) {
