@@ -164,7 +164,7 @@ def scale_to_n30(sec_per_layer_sample: float, sample_n: int, target_n: int) -> f
 def run_reference_arm(args, rank: int, world: int) -> None:
     if rank != 0:
         return
-    n = args.n + max(0, world.bit_length() - 1)
+    n = args.n + (max(0, world.bit_length() - 1) if args.weak else 0)
     sec, threads = cpu_layers_per_sec(args.steps, min(args.warmup, 1))
     sec_full = scale_to_n30(sec, CPU_SAMPLE_N, n)
     value = 1.0 / sec_full
@@ -173,7 +173,7 @@ def run_reference_arm(args, rank: int, world: int) -> None:
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sec_full, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * sec_full, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"n={n} all-to-all XY Trotter layer (first order), complex128", "n_qubits": n,
                    "pairs_per_layer": n * (n - 1) // 2, "seed": SEED},
@@ -204,20 +204,29 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
-    n = args.n
-    K, w = synthetic_problem(n, SEED + rank)
+    gbits = world.bit_length() - 1
+    n = args.n + (gbits if args.weak else 0)   # total qubits of the (sharded) state
+    K, w = synthetic_problem(n, SEED)
     tau = 0.02
 
-    eng = XYKEngine(n, device=device)
-    eng.set_problem(K, w)
-    eng.set_engine("tiled" if n >= 12 else "simple")
+    if world == 1:
+        eng = XYKEngine(n, device=device)
+        eng.set_problem(K, w)
+        eng.set_engine("tiled" if n >= 12 else "simple")
+        raw = eng
+    else:
+        from scpn_quantum_control_b200.sharded import ShardedXYKEngine
+
+        eng = ShardedXYKEngine(n, device=device)
+        eng.set_problem(K, w)
+        raw = eng.eng
     eng.init_product_state()
     for _ in range(max(args.warmup, 3)):
         eng.apply_layers(tau, 1, 1)
-    eng.synchronize()
-    eng.enable_timing(True)
+    raw.synchronize()
+    raw.enable_timing(True)
     st0 = eng.stats()
-    stream = torch.cuda.ExternalStream(eng.stream(), device=device)
+    stream = torch.cuda.ExternalStream(raw.stream(), device=device)
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     if dist is not None:
@@ -235,6 +244,8 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
     ms_total = ev0.elapsed_time(ev1)
     st1 = eng.stats()
     norm2 = eng.norm2()
+    if world > 1:
+        st1 = dict(st1)
     if dist is not None:
         t = torch.tensor([ms_total], device=f"cuda:{device}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -250,7 +261,7 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
     # ---- e2e through the public API, host buffers in, host R(t) out ----
     e2e_steps = 2
     layers_per_step = 5
-    solver = QuantumKuramotoSolver(n, K, w, evolution="trotter", device=device)
+    solver = QuantumKuramotoSolver(n, K, w, evolution="trotter", device=device, distributed=world > 1)
     solver.run(0.1 * 1, 0.1, layers_per_step)  # warm (plans, allocations)
     torch.cuda.synchronize(device)
     if dist is not None:
@@ -274,21 +285,29 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
         return
 
     peak, peak_src = measured_peak()
-    alg_bytes = 2.0 * 16.0 * 2.0 ** n
+    n_shard = n - gbits
+    alg_bytes = 2.0 * 16.0 * 2.0 ** n_shard   # per launch: one read + one write of this GPU's shard
     achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
-    value = world * 1e3 / ms_per_step  # every rank advances its own 2^n state by one layer per step
+    # one step = one first-order Trotter layer of the WHOLE n-qubit state (all ranks together)
+    value = 1e3 / ms_per_step
+    exch = {}
+    if world > 1:
+        exch = {"exchanges_per_layer": (st1["exchanges"] - st0.get("exchanges", 0)) / args.steps,
+                "exchange_ms_mean": float(np.mean(eng.exchange_log[-8:])) if eng.exchange_log else None,
+                "nvlink_bytes_per_exchange_per_gpu": int(16 * 2 ** n_shard * (world - 1) // world)}
     cpu_sec, threads = cpu_layers_per_sec(1, 1) if not args.no_cpu else (float("nan"), 0)
     cpu_sec_full = scale_to_n30(cpu_sec, CPU_SAMPLE_N, n)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"n={n} all-to-all XY Trotter layer (first order), complex128, {16 * 2 ** n / 2 ** 30:.0f} GiB state per GPU"
-                        + ("" if world == 1 else f", {world} independent replicas (sharded n={n + world.bit_length() - 1} path: see DESIGN.md)"),
+            "workload": f"n={n} all-to-all XY Trotter layer (first order), complex128, {16 * 2 ** n_shard / 2 ** 30:.2f} GiB shard per GPU"
+                        + ("" if world == 1 else f", state sharded by its top {gbits} qubits over {world} GPUs, NCCL all-to-all qubit exchanges"),
             "n_qubits": n, "pairs_per_layer": n * (n - 1) // 2, "seed": SEED, "tau": tau,
             "l2_policy": "state (16 GiB) >> L2 (126 MB): every pass streams from HBM, no flush needed",
             "passes_per_layer": passes / args.steps, "rounds_per_layer": rounds, "sweeps_per_layer": sweeps / args.steps,
+            **exch,
         },
         "roofline": {
             "bound": "hbm", "kernel": "tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -303,7 +322,7 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
                       f"(pairs({n})/pairs({CPU_SAMPLE_N})) * 2^{n - CPU_SAMPLE_N}",
         },
         "e2e": {
-            "value": world * e2e_layers / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "value": e2e_layers / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "call": f"QuantumKuramotoSolver(n, K, omega, evolution='trotter').run({0.1 * e2e_steps:.1f}, 0.1, {layers_per_step})",
             "includes": "problem upload, device state preparation, R(t) every 5 layers, read-back",
         },
@@ -324,6 +343,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=BASE_N, help="qubits per GPU (default: the headline n=30)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: --n qubits PER GPU (n=33 on 8 GPUs); default is strong scaling at n total")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -60,6 +60,7 @@ class ShardedXYKEngine:
         self.exchanges = 0
         self.exchange_seconds = 0.0
         self.exchange_bytes = 0
+        self.exchange_log: list[float] = []  # milliseconds per exchange
 
     def close(self) -> None:
         self.eng.close()
@@ -81,6 +82,7 @@ class ShardedXYKEngine:
         ev1.record()
         torch.cuda.synchronize(self.device)
         self.exchange_seconds += ev0.elapsed_time(ev1) * 1e-3
+        self.exchange_log.append(ev0.elapsed_time(ev1))
         self.exchange_bytes += bpb.value * (self.world_size - 1)
         self.exchanges += 1
         self.eng._check(lib.xyk_exchange_done(h))

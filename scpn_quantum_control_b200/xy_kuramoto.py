@@ -101,6 +101,7 @@ class QuantumKuramotoSolver:
         dtype: str = "complex128",
         device: int = 0,
         exact_tol: float = 2e-10,
+        distributed: bool = False,
     ):
         """K_coupling: (n,n) coupling matrix, omega_natural: (n,) frequencies."""
         self.n = self._validate_n_oscillators(n_oscillators)
@@ -122,7 +123,10 @@ class QuantumKuramotoSolver:
         self.dtype = dtype
         self.device = int(device)
         self.exact_tol = float(exact_tol)
-        self._engine: XYKEngine | None = None
+        # distributed=True: the state is sharded over the ranks of the default torch.distributed
+        # (NCCL) process group, one process per GPU; every rank calls the same methods
+        self.distributed = bool(distributed)
+        self._engine = None
         self._exact_reps_cache: dict[tuple[float, float], int] = {}
 
     # -- validation (same messages as the reference) ---------------------------------------------
@@ -153,10 +157,16 @@ class QuantumKuramotoSolver:
         except RuntimeError:
             free = None
         buffers = 2 if self.n > _SMALL_N else 1  # tiled passes ping-pong between two buffers
+        n_devices = 1
+        if self.distributed:
+            import torch.distributed as dist
+
+            n_devices = dist.get_world_size() if dist.is_initialized() else 1
         require_statevector_allocation(
             self.n,
             itemsize=16 if self.dtype == "complex128" else 8,
             buffers=buffers,
+            n_devices=n_devices,
             max_gib=max_statevector_gib,
             device_free_bytes=free,
             label="Kuramoto statevector trajectory",
@@ -165,7 +175,12 @@ class QuantumKuramotoSolver:
     def engine(self) -> XYKEngine:
         """The device engine holding the live statevector (created on first use)."""
         if self._engine is None:
-            eng = XYKEngine(self.n, dtype=self.dtype, device=self.device)
+            if self.distributed:
+                from .sharded import ShardedXYKEngine
+
+                eng = ShardedXYKEngine(self.n, device=self.device)
+            else:
+                eng = XYKEngine(self.n, dtype=self.dtype, device=self.device)
             eng.set_problem(self.K, self.omega)
             self._engine = eng
         return self._engine
@@ -199,7 +214,7 @@ class QuantumKuramotoSolver:
                 return v
         if step_dt == 0.0:
             return 1
-        eng = XYKEngine(self.n, dtype=self.dtype, device=self.device) if self.n <= 20 else None
+        eng = XYKEngine(self.n, dtype=self.dtype, device=self.device) if self.n <= 20 and not self.distributed else None
         if eng is None:  # calibration at large n costs too much memory: use a norm-based rule
             scale = float(np.abs(self.K).sum() / 2.0 + np.abs(self.omega).sum())
             reps = max(1, int(np.ceil(step_dt * scale / 6.0)))
@@ -288,7 +303,7 @@ class QuantumKuramotoSolver:
             for s in np.unique(np.round(step_sizes, 15)):
                 exact_reps[float(s)] = self._calibrated_exact_reps(float(s), len(step_sizes))
 
-        if self.n <= _SMALL_N and self.dtype == "complex128":
+        if self.n <= _SMALL_N and self.dtype == "complex128" and not self.distributed:
             R_history = self._run_small(step_sizes, trotter_per_step, exact_reps)
         else:
             eng = self.engine()
