@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -288,9 +289,15 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
         for (int b = 0; b < Desc::NT; ++b) d.last_thr_out[b] = (uint8_t)pp.out_of_in[pp.rounds[0].thrpos[b]];
         for (int k = 0; k < kRB; ++k) d.last_reg_out[k] = (uint8_t)pp.out_of_in[pp.rounds[0].regpos[k]];
     }
+    std::vector<PlanRound> rounds_used(pp.rounds);
+    if (h->debug_mode == 3 && pp.rounds.size() >= 2) {  // timing experiment: first + last round only, no gates
+        rounds_used = {pp.rounds.front(), pp.rounds.back()};
+        rounds_used[0].cta_sync_after = 1;
+        d.nrounds = 2;
+    }
     lift_ok = true;
     for (int r = 0; r < d.nrounds; ++r) {
-        const PlanRound& pr = pp.rounds[r];
+        const PlanRound& pr = rounds_used[r];
         for (int s = 0; s < Desc::NSLOT; ++s)
             if ((pr.mask >> s) & 1u) {
                 const double phi = std::remainder(pr.phi[s], 2.0 * M_PI);
@@ -298,7 +305,7 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
             }
     }
     for (int r = 0; r < d.nrounds; ++r) {
-        const PlanRound& pr = pp.rounds[r];
+        const PlanRound& pr = rounds_used[r];
         Desc::Round& R = d.rounds[r];
         for (int b = 0; b < Desc::NT; ++b) R.thrpos[b] = (uint8_t)pr.thrpos[b];
         for (int k = 0; k < kRB; ++k) {
@@ -349,6 +356,8 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
     cfg.TB = kTB;
     cfg.RB = kRB;
     cfg.max_rounds = kMaxRounds;
+    if (const char* e = std::getenv("XYK_LANE_BITS")) cfg.lane_bits = std::atoi(e);      // tuning experiments
+    if (const char* e = std::getenv("XYK_NEED_SHARED")) cfg.need_shared = std::atoi(e);
     prog->plan = compile_plan(h->nlocal, segs, cfg);
     prog->plan.layers1_equiv = l1;
     prog->loc2log.resize(h->nlocal);
@@ -448,22 +457,56 @@ bool use_tiled(xyk_handle h) {
     return h->nlocal >= 13;
 }
 
-// <X_q>, <Y_q> for local qubits -> d_out[2q], d_out[2q+1] (already multiplied by 2)
+template <typename real, int M>
+void launch_obs_multi(xyk_handle h, const ObsSpec& S, int grid) {
+    using C = typename cplx<real>::type;
+    xy_expect_multi_kernel<real, M><<<grid, 256, 0, h->stream>>>((const C*)h->buf[h->cur], S, (double2*)h->d_partial);
+}
+
+// <X_q>, <Y_q> for local qubits -> d_out[2q], d_out[2q+1] (already multiplied by 2).
+// Five qubits per sweep (each thread holds the 32 amplitudes they span): ceil(n_local / 5) reads of the
+// state instead of the n reads of the per-qubit loop (reference: pauli.rs:195-211 does n passes).
 int xy_expect_device(xyk_handle h) {
-    const uint64_t half = 1ull << (h->nlocal - 1);
-    const int grid = std::min(kRedBlocks, grid_for(h, half, 256));
+    const int grid_cap = kRedBlocks;
+    std::vector<std::pair<int, int>> loc;  // (physical position, logical qubit)
     for (int q = 0; q < h->n; ++q) {
-        const int pos = h->perm[q];
-        double2* part = (double2*)h->d_partial + (size_t)q * kRedBlocks;
-        if (pos >= h->nlocal) {  // sharded qubit: reported as 0 here, the host measures it after an exchange
-            cudaMemsetAsync(part, 0, sizeof(double2) * grid, h->stream);
-            continue;
+        if (h->perm[q] < h->nlocal) loc.push_back({h->perm[q], q});
+        else cudaMemsetAsync((double2*)h->d_partial + (size_t)q * kRedBlocks, 0, sizeof(double2) * kRedBlocks, h->stream);
+    }
+    std::sort(loc.begin(), loc.end());
+    const bool multi = h->tiled_obs && h->nlocal >= 10;
+    // one grid size for every launch of this call (the finalize stage sums `grid` partials per row)
+    const int Mmax = multi ? (int)std::min<size_t>(5, loc.size()) : 1;
+    const int grid = std::max(1, std::min(grid_cap, grid_for(h, 1ull << (h->nlocal - Mmax), 256)));
+    size_t i = 0;
+    while (i < loc.size()) {
+        const int M = multi ? (int)std::min<size_t>(5, loc.size() - i) : 1;
+        ObsSpec S{};
+        S.nlocal = h->nlocal;
+        S.stride = kRedBlocks;
+        for (int m = 0; m < M; ++m) {
+            S.pos[m] = loc[i + m].first;
+            S.qidx[m] = loc[i + m].second;
         }
-        if (h->dtype == 0)
-            xy_expect_kernel<double><<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], h->nlocal, pos, part);
-        else
-            xy_expect_kernel<float><<<grid, 256, 0, h->stream>>>((const float2*)h->buf[h->cur], h->nlocal, pos, part);
+        if (h->dtype == 0) {
+            switch (M) {
+                case 1: launch_obs_multi<double, 1>(h, S, grid); break;
+                case 2: launch_obs_multi<double, 2>(h, S, grid); break;
+                case 3: launch_obs_multi<double, 3>(h, S, grid); break;
+                case 4: launch_obs_multi<double, 4>(h, S, grid); break;
+                default: launch_obs_multi<double, 5>(h, S, grid); break;
+            }
+        } else {
+            switch (M) {
+                case 1: launch_obs_multi<float, 1>(h, S, grid); break;
+                case 2: launch_obs_multi<float, 2>(h, S, grid); break;
+                case 3: launch_obs_multi<float, 3>(h, S, grid); break;
+                case 4: launch_obs_multi<float, 4>(h, S, grid); break;
+                default: launch_obs_multi<float, 5>(h, S, grid); break;
+            }
+        }
         h->stats.kernel_launches++;
+        i += M;
     }
     xy_finalize_kernel<<<h->n, 128, 0, h->stream>>>((const double2*)h->d_partial, grid, kRedBlocks, h->d_out);
     h->stats.kernel_launches++;

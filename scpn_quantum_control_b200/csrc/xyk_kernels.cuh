@@ -198,6 +198,60 @@ __global__ void xy_expect_kernel(const typename cplx<real>::type* __restrict__ p
     if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(acc[0], acc[1]);
 }
 
+// <X>, <Y> of M qubits in ONE sweep: each thread holds the 2^M amplitudes spanned by the M physical
+// bits pos[0..M) (ascending) of one base index and accumulates, for every m, the pair products over
+// the 2^(M-1) pairs that differ in bit m.  partial[(qidx[m]) * stride + blockIdx.x] = (Re, Im) sums.
+struct ObsSpec {
+    int32_t pos[8];    // physical bits, ascending
+    int32_t qidx[8];   // row of `partial` each one reports to
+    int32_t nlocal;
+    int32_t stride;
+};
+
+template <typename real, int M>
+__global__ void __launch_bounds__(256) xy_expect_multi_kernel(const typename cplx<real>::type* __restrict__ psi,
+                                                              const __grid_constant__ ObsSpec S,
+                                                              double2* __restrict__ partial) {
+    constexpr int NA = 1 << M;
+    __shared__ double red[2 * M * 32];
+    const uint64_t nbase = 1ull << (S.nlocal - M);
+    double acc[2 * M];
+#pragma unroll
+    for (int k = 0; k < 2 * M; ++k) acc[k] = 0.0;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbase; b += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t k0 = b;
+#pragma unroll
+        for (int m = 0; m < M; ++m) k0 = insert_zero64(k0, S.pos[m]);
+        double ar[NA], ai[NA];
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            uint64_t off = 0;
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                if ((j >> m) & 1) off |= 1ull << S.pos[m];
+            const typename cplx<real>::type v = psi[k0 | off];
+            ar[j] = (double)v.x;
+            ai[j] = (double)v.y;
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+#pragma unroll
+            for (int j = 0; j < NA; ++j) {
+                if (!((j >> m) & 1)) {
+                    const int f = j | (1 << m);
+                    acc[2 * m] += ar[j] * ar[f] + ai[j] * ai[f];
+                    acc[2 * m + 1] += ar[j] * ai[f] - ai[j] * ar[f];
+                }
+            }
+        }
+    }
+    block_sum<2 * M>(acc, red);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            partial[(size_t)S.qidx[m] * S.stride + blockIdx.x] = make_double2(acc[2 * m], acc[2 * m + 1]);
+}
+
 // partial[blockIdx.x][b] = sum_k (1 - 2 bit_b(k)) |psi_k|^2 for every physical bit b < nlocal,
 // partial[blockIdx.x][nlocal] = sum_k |psi_k|^2     (pauli.rs:163-170)
 template <typename real>

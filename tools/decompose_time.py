@@ -10,7 +10,7 @@ K, w = oc.random_problem(n, 20260700 + n)
 with XYKEngine(n) as eng:
     eng.set_problem(K, w)
     eng.set_engine("tiled")
-    for mode in (0, 1, 2, 0):
+    for mode in (0, 1, 3, 0):
         eng.set_option(100, mode)
         eng.init_product_state()
         eng.enable_timing(True)
