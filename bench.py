@@ -311,7 +311,7 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
         },
         "roofline": {
             "bound": "hbm", "kernel": "tile_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(n),
+            "frac": achieved / peak, "peak_source": peak_src, "traffic": ncu_traffic(n_shard),
             "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": pass_ms,
             "layer_algorithmic_frac": (1e3 / ms_per_step) * alg_bytes / 1e9 / peak,
             "layer_sweeps_frac": (1e3 / ms_per_step) * (sweeps / args.steps) * alg_bytes / 1e9 / peak,
