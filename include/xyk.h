@@ -40,6 +40,7 @@ typedef struct xyk_handle_s *xyk_handle;
 #define XYK_ERR_STATE 4       /* call sequence error (e.g. no problem set)      */
 #define XYK_ERR_UNSUPPORTED 5 /* configuration not supported by this build      */
 #define XYK_NEED_EXCHANGE 100 /* sharded run: host must perform the all-to-all  */
+#define XYK_NEED_BARRIER 101  /* sharded run: host must fence all ranks (device sync + barrier), then xyk_continue */
 
 /* engines (xyk_set_option(h, XYK_OPT_ENGINE, v)) */
 #define XYK_ENGINE_AUTO 0   /* tiled for n_local >= 13, gate-by-gate below          */
@@ -48,7 +49,9 @@ typedef struct xyk_handle_s *xyk_handle;
 
 #define XYK_OPT_ENGINE 1
 #define XYK_OPT_FUSE_PHASE 2   /* 1 (default): Z phase folded into the first pass of a layer */
-#define XYK_OPT_TILED_OBS 3    /* 1 (default): tile-based observable sweeps                  */
+#define XYK_OPT_TILED_OBS 3    /* 1 (default): five qubits per observable sweep              */
+#define XYK_OPT_PEER_EXCHANGE 4 /* 1 (default): fuse exchanges into the preceding pass (peer stores over NVLink)
+                                  when the ranks' buffers have been mapped with xyk_ipc_export/import */
 
 int xyk_version(void);
 const char *xyk_last_error(xyk_handle h);
@@ -94,6 +97,12 @@ int xyk_exchange_done(xyk_handle h);
  * the g = log2(world_size) logical qubits outgoing[0..g) leave, the sharded ones arrive.
  * Returns XYK_NEED_EXCHANGE; the host then proceeds as above. */
 int xyk_begin_exchange(xyk_handle h, const int *outgoing);
+/* Map the two state buffers of every rank into this process (CUDA IPC, 64-byte handles exchanged by
+ * the host).  Once all ranks' buffers are imported, an exchange that follows a pass is executed BY
+ * that pass: its store scatters directly into the destination ranks' buffers over NVLink; the C ABI
+ * then returns XYK_NEED_BARRIER before and after that pass instead of XYK_NEED_EXCHANGE. */
+int xyk_ipc_export(xyk_handle h, int which, unsigned char *handle64);
+int xyk_ipc_import(xyk_handle h, int peer_rank, int which, const unsigned char *handle64);
 
 /* <X_q>, <Y_q> for every qubit (partial sums over this shard for sharded handles: the host
  * adds the per-rank arrays).  Qubits that are currently global on a sharded handle are

@@ -20,9 +20,10 @@ XYK_ERR_NOMEM = 3
 XYK_ERR_STATE = 4
 XYK_ERR_UNSUPPORTED = 5
 XYK_NEED_EXCHANGE = 100
+XYK_NEED_BARRIER = 101
 
 ENGINE_AUTO, ENGINE_SIMPLE, ENGINE_TILED = 0, 1, 2
-OPT_ENGINE, OPT_FUSE_PHASE, OPT_TILED_OBS = 1, 2, 3
+OPT_ENGINE, OPT_FUSE_PHASE, OPT_TILED_OBS, OPT_PEER_EXCHANGE = 1, 2, 3, 4
 
 
 class XYKLibraryError(RuntimeError):
@@ -62,6 +63,8 @@ PROTOTYPES = {
     "xyk_exchange_info": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t)]),
     "xyk_exchange_done": (c_int, [c_void_p]),
     "xyk_begin_exchange": (c_int, [c_void_p, POINTER(c_int)]),
+    "xyk_ipc_export": (c_int, [c_void_p, c_int, c_char_p]),
+    "xyk_ipc_import": (c_int, [c_void_p, c_int, c_int, c_char_p]),
     "xyk_xy_expectations": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "xyk_order_parameter": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "xyk_z_expectations": (c_int, [c_void_p, POINTER(c_double)]),

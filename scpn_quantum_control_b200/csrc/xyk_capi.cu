@@ -40,6 +40,8 @@ struct ShardStep {
     bool is_exchange = false;
     std::shared_ptr<Program> prog;
     std::vector<int> outgoing, incoming;
+    bool peer_last = false;            // the last pass carries the exchange (peer stores)
+    std::vector<int> rank_out;         // local output bit of the qubit arriving from rank bit k
 };
 
 }  // namespace
@@ -77,6 +79,11 @@ struct xyk_handle_s {
     bool exchange_pending = false;
     std::vector<int> ex_out, ex_in;
     int64_t exchanges = 0;
+    int shard_phase = 0;               // progress inside a step whose last pass is a peer pass
+    void* peer_buf[8][2] = {};         // state buffers of every rank (own pointers for rank == this rank)
+    bool peer_open[8][2] = {};
+    bool peers_ready = false;
+    int peer_exchange_opt = 1;
     std::string err;
 };
 
@@ -370,34 +377,43 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
 
 int configure_pass_kernels(xyk_handle h) {
     const int smem = (1 << kTB) * 16;
-    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, true, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
-    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_pass_kernel<kTB, kRB, true, 3>, 1 << (kTB - kRB), smem));
+    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_pass_kernel<kTB, kRB, true, 3, false>, 1 << (kTB - kRB), smem));
     if (occ < 1) occ = 1;
     h->pass_grid = occ * h->sm_count;
     return XYK_OK;
 }
 
-int run_program_tiled(xyk_handle h, Program& prog) {
-    const Plan& plan = prog.plan;
+// prepare buffers / layout for a program (idempotent)
+int begin_program(xyk_handle h, Program& prog) {
     int rc = ensure_alt(h);
     if (rc) return rc;
     if (!h->pass_grid) {
         rc = configure_pass_kernels(h);
         if (rc) return rc;
     }
-    {
-        std::vector<int> target(h->perm);
-        for (int l = 0; l < plan.nq; ++l) target[prog.loc2log[l]] = plan.start_perm[l];
-        rc = relayout(h, target);
-        if (rc) return rc;
-    }
+    std::vector<int> target(h->perm);
+    for (int l = 0; l < prog.plan.nq; ++l) target[prog.loc2log[l]] = prog.plan.start_perm[l];
+    return relayout(h, target);
+}
+
+// passes [p0, p1) of a program.  peer = true: the (single) pass scatters into the mapped buffers of
+// every rank (the exchange fused into the store); the caller has fenced the ranks around it.
+int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
+    const Plan& plan = prog.plan;
     const uint64_t ntiles = 1ull << (h->nlocal - kTB);
     const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)h->pass_grid);
     const int smem = (1 << kTB) * 16;
-    if (h->stats.timing_enabled) cudaEventRecord(h->ev0, h->stream);
-    for (size_t p = 0; p < plan.passes.size(); ++p) {
+    const int nthr = 1 << (kTB - kRB);
+    PeerPtrs peers{};
+    if (peer)
+        for (int r = 0; r < h->world; ++r) peers.p[r] = (double2*)h->peer_buf[r][h->cur ^ 1];
+    int rc;
+    for (size_t p = p0; p < p1; ++p) {
         const PlanPass& pp = plan.passes[p];
         if (pp.has_phase && !(prog.descs[p].flags & kPassHasPhase)) {
             rc = apply_phase(h, pp.ztau);
@@ -413,10 +429,13 @@ int run_program_tiled(xyk_handle h, Program& prog) {
             }
             cudaEventRecord(h->pass_events[2 * p], h->stream);
         }
-        if (prog.lift[p])
-            tile_pass_kernel<kTB, kRB, true, 3><<<grid, 1 << (kTB - kRB), smem, h->stream>>>(in, out, prog.descs[p], ntiles);
-        else
-            tile_pass_kernel<kTB, kRB, false, 3><<<grid, 1 << (kTB - kRB), smem, h->stream>>>(in, out, prog.descs[p], ntiles);
+        if (peer) {
+            if (prog.lift[p]) tile_pass_kernel<kTB, kRB, true, 3, true><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
+            else tile_pass_kernel<kTB, kRB, false, 3, true><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
+        } else {
+            if (prog.lift[p]) tile_pass_kernel<kTB, kRB, true, 3, false><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
+            else tile_pass_kernel<kTB, kRB, false, 3, false><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
+        }
         if (h->stats.timing_enabled) cudaEventRecord(h->pass_events[2 * p + 1], h->stream);
         h->cur ^= 1;
         std::vector<int> np(h->perm);
@@ -426,15 +445,21 @@ int run_program_tiled(xyk_handle h, Program& prog) {
         h->stats.pass_launches++;
         h->stats.state_sweeps++;
     }
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
+int end_program(xyk_handle h, Program& prog, size_t timed_passes) {
+    const Plan& plan = prog.plan;
     if (plan.has_trailing_phase) {
-        rc = apply_phase(h, plan.trailing_ztau);
+        int rc = apply_phase(h, plan.trailing_ztau);
         if (rc) return rc;
     }
     if (h->stats.timing_enabled) {
         cudaEventRecord(h->ev1, h->stream);
         cudaEventSynchronize(h->ev1);
         cudaEventElapsedTime(&h->stats.last_pass_ms, h->ev0, h->ev1);
-        for (size_t p = 0; p < plan.passes.size(); ++p) {
+        for (size_t p = 0; p < timed_passes; ++p) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, h->pass_events[2 * p], h->pass_events[2 * p + 1]);
             h->stats.pass_kernel_ms += ms;
@@ -442,10 +467,21 @@ int run_program_tiled(xyk_handle h, Program& prog) {
         }
     }
     XYK_CUDA(h, cudaGetLastError());
-    h->stats.last_passes = (int)plan.passes.size();
-    h->stats.last_rounds = plan.total_rounds;
-    h->stats.last_gates = plan.total_gates;
-    h->stats.last_layers1 = plan.layers1_equiv;
+    return XYK_OK;
+}
+
+int run_program_tiled(xyk_handle h, Program& prog) {
+    int rc = begin_program(h, prog);
+    if (rc) return rc;
+    if (h->stats.timing_enabled) cudaEventRecord(h->ev0, h->stream);
+    rc = run_passes(h, prog, 0, prog.plan.passes.size(), false);
+    if (rc) return rc;
+    rc = end_program(h, prog, prog.plan.passes.size());
+    if (rc) return rc;
+    h->stats.last_passes = (int)prog.plan.passes.size();
+    h->stats.last_rounds = prog.plan.total_rounds;
+    h->stats.last_gates = prog.plan.total_gates;
+    h->stats.last_layers1 = prog.plan.layers1_equiv;
     return XYK_OK;
 }
 
@@ -541,8 +577,37 @@ int run_shard_steps(xyk_handle h) {
     while (h->shard_pos < h->shard_steps.size()) {
         ShardStep& st = h->shard_steps[h->shard_pos];
         if (!st.is_exchange) {
-            int rc = run_program_tiled(h, *st.prog);
+            Program& prog = *st.prog;
+            const size_t P = prog.plan.passes.size();
+            if (!st.peer_last) {
+                int rc = run_program_tiled(h, prog);
+                if (rc) return rc;
+                h->shard_pos++;
+                continue;
+            }
+            if (h->shard_phase == 0) {  // everything but the last pass, then fence the ranks
+                int rc = begin_program(h, prog);
+                if (rc) return rc;
+                if (h->stats.timing_enabled) cudaEventRecord(h->ev0, h->stream);
+                rc = run_passes(h, prog, 0, P - 1, false);
+                if (rc) return rc;
+                XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+                h->shard_phase = 1;
+                return XYK_NEED_BARRIER;  // every rank is done reading the buffer its peers will overwrite
+            }
+            if (h->shard_phase == 1) {  // the pass that scatters into every rank's spare buffer
+                const std::vector<int> in_glob = current_globals(h);
+                int rc = run_passes(h, prog, P - 1, P, true);
+                if (rc) return rc;
+                for (int k = 0; k < h->gbits; ++k) h->perm[in_glob[k]] = st.rank_out[k];  // arrived from rank bit k
+                XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+                h->exchanges++;
+                h->shard_phase = 2;
+                return XYK_NEED_BARRIER;  // every rank's stores have landed
+            }
+            int rc = end_program(h, prog, P);
             if (rc) return rc;
+            h->shard_phase = 0;
             h->shard_pos++;
             continue;
         }
@@ -560,6 +625,7 @@ int run_shard_steps(xyk_handle h) {
     }
     h->shard_steps.clear();
     h->shard_pos = 0;
+    h->shard_phase = 0;
     return XYK_OK;
 }
 
@@ -568,6 +634,7 @@ int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1) {
     cfg.TB = kTB;
     cfg.RB = kRB;
     cfg.max_rounds = kMaxRounds;
+    cfg.peer_exchange = h->peers_ready && h->peer_exchange_opt;
     std::vector<ShardOp> ops;
     try {
         ops = compile_sharded(h->n, current_globals(h), segs, cfg, nullptr);
@@ -596,6 +663,19 @@ int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1) {
             st.prog->plan.layers1_equiv = 0;
             st.prog->loc2log = op.loc2log;
             finish_program(h, *st.prog);
+            if (op.peer_last) {
+                st.peer_last = true;
+                st.rank_out = op.rank_out;
+                uint64_t ob = 0;
+                for (int k = 0; k < h->gbits; ++k)
+                    if ((h->rank >> k) & 1) ob |= 1ull << op.rank_out[k];
+                st.prog->descs.back().out_base = ob;
+                // descriptor phase constants of later programs need the post-exchange rank bits
+                for (int k = 0; k < h->gbits; ++k) {
+                    h->perm[op.outgoing_fused[k]] = h->nlocal + k;
+                    h->perm[op.incoming_fused[k]] = op.rank_out[k];
+                }
+            }
             gates += st.prog->plan.total_gates;
             rounds += st.prog->plan.total_rounds;
             passes += (int)st.prog->plan.passes.size();
@@ -692,6 +772,9 @@ int xyk_destroy(xyk_handle h) {
     if (!h) return XYK_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < 8; ++r)
+        for (int w = 0; w < 2; ++w)
+            if (h->peer_open[r][w]) cudaIpcCloseMemHandle(h->peer_buf[r][w]);
     for (int b = 0; b < 2; ++b)
         if (h->buf[b]) cudaFree(h->buf[b]);
     if (h->d_tab) cudaFree(h->d_tab);
@@ -718,6 +801,9 @@ int xyk_set_option(xyk_handle h, int option, int64_t value) {
             return XYK_OK;
         case XYK_OPT_TILED_OBS:
             h->tiled_obs = value != 0;
+            return XYK_OK;
+        case XYK_OPT_PEER_EXCHANGE:
+            h->peer_exchange_opt = value != 0;
             return XYK_OK;
         case 100:
             h->debug_mode = (int)value;
@@ -828,6 +914,39 @@ int xyk_exchange_done(xyk_handle h) {
     h->exchanges++;
     h->stats.state_sweeps++;
     if (h->shard_pos < h->shard_steps.size() && h->shard_steps[h->shard_pos].is_exchange) h->shard_pos++;
+    return XYK_OK;
+}
+
+int xyk_ipc_export(xyk_handle h, int which, unsigned char* handle64) {
+    if (!h || !handle64 || which < 0 || which > 1) return XYK_ERR_INVALID;
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_alt(h);
+    if (rc) return rc;
+    cudaIpcMemHandle_t mh;
+    XYK_CUDA(h, cudaIpcGetMemHandle(&mh, h->buf[which]));
+    static_assert(sizeof(mh) == 64, "CUDA IPC handle is 64 bytes");
+    std::memcpy(handle64, &mh, 64);
+    return XYK_OK;
+}
+
+int xyk_ipc_import(xyk_handle h, int peer_rank, int which, const unsigned char* handle64) {
+    if (!h || !handle64 || which < 0 || which > 1 || peer_rank < 0 || peer_rank >= h->world || peer_rank >= 8)
+        return XYK_ERR_INVALID;
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    if (peer_rank == h->rank) {
+        h->peer_buf[peer_rank][which] = h->buf[which];
+    } else {
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, handle64, 64);
+        void* p = nullptr;
+        XYK_CUDA(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_buf[peer_rank][which] = p;
+        h->peer_open[peer_rank][which] = true;
+    }
+    bool all = true;
+    for (int r = 0; r < h->world; ++r)
+        for (int w = 0; w < 2; ++w) all &= h->peer_buf[r][w] != nullptr;
+    h->peers_ready = all;
     return XYK_OK;
 }
 
@@ -1087,7 +1206,6 @@ int xyk_enable_timing(xyk_handle h, int on) {
 
 int64_t xyk_plan_describe(int n_local, int dtype, const double* K, const double* omega, int n, double delta,
                           int order, int reps, char* buf, int64_t cap) {
-    (void)dtype;
     if (n < 1 || n > kMaxQ || n_local < 1 || n_local > n || !K || !omega) return -1;
     try {
         std::vector<PairTerm> pairs;
@@ -1100,9 +1218,17 @@ int64_t xyk_plan_describe(int n_local, int dtype, const double* K, const double*
         cfg.TB = kTB;
         cfg.RB = kRB;
         cfg.max_rounds = kMaxRounds;
-        Plan plan = compile_plan(n_local, segs, cfg);
-        plan.layers1_equiv = l1;
-        const std::string js = plan_to_json(plan);
+        std::string js;
+        if (n_local < n) {  // sharded program: the g highest logical qubits start on the rank bits
+            std::vector<int> glob;
+            for (int q = n_local; q < n; ++q) glob.push_back(q);
+            cfg.peer_exchange = (dtype & 2) != 0;  // test hook: bit 1 of `dtype` selects fused (peer-store) exchanges
+            js = sharded_to_json(compile_sharded(n, glob, segs, cfg, nullptr));
+        } else {
+            Plan plan = compile_plan(n_local, segs, cfg);
+            plan.layers1_equiv = l1;
+            js = plan_to_json(plan);
+        }
         if (buf && cap > (int64_t)js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
         return (int64_t)js.size() + 1;
     } catch (const std::exception& e) {

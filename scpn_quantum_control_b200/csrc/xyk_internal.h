@@ -83,7 +83,12 @@ struct SchedConfig {
     int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
     bool cyclic = true;    // the program ends in its own start layout (it can be replayed back to back)
+    bool peer_exchange = false;  // sharded: fuse exchanges into the preceding pass (needs mapped peer buffers)
     std::vector<int> final_top;  // non-cyclic: qubits that must end on the highest physical bits, in this order
+    // open programs chained across an exchange that is fused into the last pass's store:
+    uint64_t next_tile_hint = 0;        // qubits (local indices) of the NEXT program's first tile that are local here
+    std::vector<int> final_positions;   // explicit output bit of every local index after the last pass
+                                        // (>= nq: the qubit leaves to rank bit (position - nq))
 };
 
 // Compile the segments into tile passes over nq local qubits.  Throws std::runtime_error.
@@ -100,6 +105,10 @@ std::string plan_to_json(const Plan& plan);
 // ---- sharded state (top g physical bits = rank): local programs separated by exchanges ----
 struct ShardOp {
     bool is_exchange = false;
+    // the exchange that follows this local program is fused into its last pass (peer stores):
+    bool peer_last = false;
+    std::vector<int> rank_out;  // peer_last: output bit (local) of the qubit currently on rank bit k
+    std::vector<int> outgoing_fused, incoming_fused;
     // local program
     std::vector<int> loc2log;   // logical qubit of local index l (ascending)
     Plan plan;                  // over local indices

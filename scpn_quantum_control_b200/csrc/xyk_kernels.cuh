@@ -407,6 +407,7 @@ struct PassDesc {
     uint8_t st_odst[16];     //                that output bit
     uint8_t last_thr_out[8]; // fused store: output bit of the qubit on thread bit b of the LAST round
     uint8_t last_reg_out[8]; //              output bit of the qubit on register bit k of the LAST round
+    uint64_t out_base;       // peer passes: output-index contribution of this device's rank bits
     double ph_const;         // fused phase: contribution of the sharded (rank) bits, constant on this device
     double ph_tau;           // fused phase: exp(+i tau sum_b w_b (1 - 2 bit_b)) over all input bits
     double ph_w[kMaxQ];      // omega of the logical qubit on INPUT physical bit b
@@ -446,10 +447,28 @@ __device__ __forceinline__ void sts128(uint32_t addr, const double2& v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
 }
 
-template <int TB, int RB, bool LIFT, int MINB>
+// Output buffers of every rank of a sharded state (mapped through CUDA IPC): a pass whose store is
+// fused with the qubit exchange writes each amplitude into the rank selected by the output-index
+// bits >= n_local (st.global on peer memory over NVLink) -- compute and collective in one kernel.
+struct PeerPtrs {
+    double2* p[8];
+};
+
+template <bool PEER>
+__device__ __forceinline__ void store_out(double2* __restrict__ out, const PeerPtrs& peers, int nl, uint64_t addr,
+                                          const double2& v) {
+    if constexpr (PEER) {
+        double2* base = peers.p[addr >> nl];
+        __stcs(base + (addr & ((1ull << nl) - 1ull)), v);
+    } else {
+        __stcs(out + addr, v);
+    }
+}
+
+template <int TB, int RB, bool LIFT, int MINB, bool PEER>
 __global__ void __launch_bounds__(1 << (TB - RB), MINB)
 tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
-                 const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles) {
+                 const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles, const __grid_constant__ PeerPtrs peers) {
     constexpr int NT = TB - RB, NTHR = 1 << NT, NREG = 1 << RB;
     using Round = typename PassDesc<TB, RB>::Round;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -504,7 +523,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
         const double2* src = in + (t << TB);
         // pull the next tile of this CTA into L2 while this one is being processed
         if (tid == 0 && t + gridDim.x < ntiles) prefetch_l2_bulk(in + ((t + gridDim.x) << TB), (uint32_t)(sizeof(double2) << TB));
-        uint64_t obase = 0;
+        uint64_t obase = P.out_base;
         for (int b = 0; b < P.nq - TB; ++b)
             if ((t >> b) & 1ull) obase |= 1ull << P.hi_out[b];
         uint32_t base_next = base_tab[0][tid];
@@ -595,14 +614,14 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             }
 
             if (r == nr - 1 && (flags & kPassFuseStore)) {
-                double2* dst = out + obase + st_d;
+                const uint64_t dbase = obase + st_d;
 #pragma unroll
                 for (int j = 0; j < NREG; ++j) {
                     uint64_t off = 0;
 #pragma unroll
                     for (int k = 0; k < RB; ++k)
                         if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
-                    __stcs(dst + off, a[j]);
+                    store_out<PEER>(out, peers, P.nq, dbase + off, a[j]);
                 }
             } else {
                 // tile boundary: the previous tile's last round (other warps) must be done reading
@@ -622,7 +641,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 
         if (!(flags & kPassFuseStore)) {
             // ---- store through the bit permutation, staged in shared memory ----
-            double2* dst = out + obase + st_d;
+            const uint64_t dbase = obase + st_d;
 #pragma unroll
             for (int k = 0; k < NREG; ++k) {
                 uint32_t lk = 0;
@@ -633,7 +652,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                         lk |= 1u << P.st_lsrc[NT + b];
                         dk |= 1ull << P.st_odst[NT + b];
                     }
-                __stcs(dst + dk, tile[st_l ^ swz<TB>(lk)]);
+                store_out<PEER>(out, peers, P.nq, dbase + dk, tile[st_l ^ swz<TB>(lk)]);
             }
         }
     }

@@ -279,7 +279,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // cyclic closure: the last tile must share `need` qubits with the first one so that the
     // program can be replayed from its own end layout.  If it does not, peel gates off the last
     // pass(es) and re-plan them with the extra constraint.
-    if (cfg.cyclic && !raw.empty() && popc(raw.back().tmask & first_tile) < need && nq > TB) {
+    if (!cfg.cyclic) first_tile = cfg.next_tile_hint;  // open program: share with the next program's first tile
+    if (first_tile && !raw.empty() && popc(raw.back().tmask & first_tile) < std::min(need, popc(first_tile)) && nq > TB) {
         const int s = raw.back().seg;
         const std::vector<Gate>& g = sg[s];
         // undo the last pass of segment s and re-plan the remaining gates of s
@@ -294,7 +295,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         int first = 0;
         while (ndone < g.size()) {
             while (done[first]) ++first;
-            uint64_t T = grow_tile(g, done, first, prev_tile, first_tile, need, need);
+            uint64_t T = grow_tile(g, done, first, prev_tile, first_tile, need, std::min(need, popc(first_tile)));
             RawPass rp;
             rp.tmask = T;
             rp.seg = s;
@@ -320,7 +321,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     auto next_tile = [&](int p) -> uint64_t {
         if (P == 1 && cfg.cyclic) return 0;
         if (p + 1 < P) return raw[p + 1].tmask;
-        return cfg.cyclic ? raw[0].tmask : 0;
+        return cfg.cyclic ? raw[0].tmask : cfg.next_tile_hint;
     };
     auto prev_index = [&](int p) -> int {
         if (p > 0) return p - 1;
@@ -480,6 +481,21 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         nfree[P] = nfree[0];
         plan.start_perm = layouts[0];
         plan.end_perm = layouts[0];
+    } else if (P > 0 && !cfg.final_positions.empty()) {
+        // open program chained to the next one: the caller dictates where every qubit lands
+        layouts[P] = cfg.final_positions;
+        int lowrun = 0;  // lowest output bits occupied by qubits of the last tile
+        for (int b = 0; b < nq; ++b) {
+            bool hit = false;
+            for (int q = 0; q < nq; ++q)
+                if (cfg.final_positions[q] == b && ((raw[P - 1].tmask >> q) & 1)) hit = true;
+            if (!hit) break;
+            ++lowrun;
+        }
+        nshared[P] = lowrun;
+        nfree[P] = lowrun;
+        plan.start_perm = layouts[0];
+        plan.end_perm = layouts[P];
     } else if (P > 0) {
         // open program: the last pass keeps its tile qubits low (those its last round does not hold in
         // registers first, so that the store stays coalesced) and parks `final_top` on the highest bits
@@ -542,11 +558,11 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         bool fl = cfg.fuse_io && nq > TB, fs = cfg.fuse_io && nq > TB;
         for (int b = 0; b < c_lane && fl; ++b) fl = !((rfirst[p] >> inv[b]) & 1);
         {
-            std::vector<int> inv_next(nq);
+            std::vector<int> inv_next(kMaxQ + 8, -1);
             for (int q = 0; q < nq; ++q) inv_next[layouts[p + 1][q]] = q;
             for (int b = 0; b < c_lane && fs; ++b) {
                 const int q = inv_next[b];
-                fs = ((rp.tmask >> q) & 1) && !((rlast[p] >> q) & 1);
+                fs = q >= 0 && ((rp.tmask >> q) & 1) && !((rlast[p] >> q) & 1);
             }
         }
         if (nrounds == 1 && fl) fs = false;  // one round cannot serve both lane mappings
@@ -562,8 +578,6 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         std::vector<uint64_t> wsel(nrounds, 0);
         std::vector<uint64_t> forced(nrounds, 0);  // qubits that must be LANE bits in that round
         {
-            std::vector<int> inv_next(nq);
-            for (int q = 0; q < nq; ++q) inv_next[layouts[p + 1][q]] = q;
             if (fl)
                 for (int b = 0; b < c_lane; ++b) forced[0] |= 1ull << inv[b];
             if (fs) {
@@ -712,15 +726,23 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
     const int nl = n - g;
     if (nl < 1) throw std::runtime_error("compile_sharded: no local qubits");
     std::vector<int> glob(global_qubits);
-    std::vector<ShardOp> ops;
     // flattened sequence for next-use look-ahead
-    struct FG { int i, j, seg, idx; };
+    struct FG { int i, j; };
     std::vector<FG> flat;
     for (size_t s = 0; s < segs.size(); ++s)
-        for (size_t k = 0; k < segs[s].gates.size(); ++k) flat.push_back({segs[s].gates[k].i, segs[s].gates[k].j, (int)s, (int)k});
+        for (size_t k = 0; k < segs[s].gates.size(); ++k) flat.push_back({segs[s].gates[k].i, segs[s].gates[k].j});
     std::vector<char> fdone(flat.size(), 0);
     size_t fpos = 0;  // first flat index of the current segment
 
+    // ---- phase A: which gates run between which exchanges (no plans yet) ----
+    struct Chunk {
+        std::vector<int> loc2log, log2loc;
+        Segment sub;                      // gates relabelled to local indices
+        bool has_work = false;
+        bool exchange_after = false;
+        std::vector<int> outgoing, incoming;
+    };
+    std::vector<Chunk> chunks;
     for (size_t s = 0; s < segs.size(); ++s) {
         const std::vector<GateOp>& gs = segs[s].gates;
         std::vector<char> done(gs.size(), 0);
@@ -729,14 +751,12 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
         while (true) {
             uint64_t gmask = 0;
             for (int q : glob) gmask |= 1ull << q;
-            std::vector<int> loc2log;
+            Chunk ch;
             for (int q = 0; q < n; ++q)
-                if (!((gmask >> q) & 1)) loc2log.push_back(q);
-            std::vector<int> log2loc(n, -1);
-            for (int l = 0; l < nl; ++l) log2loc[loc2log[l]] = l;
-            // closure of the pending gates of this segment over the local qubits
-            Segment sub;
-            sub.ztau = first ? segs[s].ztau : 0.0;
+                if (!((gmask >> q) & 1)) ch.loc2log.push_back(q);
+            ch.log2loc.assign(n, -1);
+            for (int l = 0; l < nl; ++l) ch.log2loc[ch.loc2log[l]] = l;
+            ch.sub.ztau = first ? segs[s].ztau : 0.0;
             std::vector<int> taken;
             {
                 uint64_t blocked = 0;
@@ -749,54 +769,101 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
             }
             for (int k : taken) {
                 GateOp go = gs[k];
-                go.i = log2loc[gs[k].i];
-                go.j = log2loc[gs[k].j];
-                sub.gates.push_back(go);
+                go.i = ch.log2loc[gs[k].i];
+                go.j = ch.log2loc[gs[k].j];
+                ch.sub.gates.push_back(go);
                 done[k] = 1;
                 fdone[fpos + k] = 1;
             }
             ndone += taken.size();
             const bool seg_finished = ndone == gs.size();
-            // which qubits leave at the next exchange (if any): furthest next use over the whole sequence
-            std::vector<int> outgoing;
+            ch.has_work = !ch.sub.gates.empty() || (first && ch.sub.ztau != 0.0);
             if (!seg_finished) {
+                // the g local qubits whose next use lies furthest ahead leave
                 std::vector<size_t> next_use(n, flat.size() + 1);
                 for (size_t f = flat.size(); f-- > 0;)
                     if (!fdone[f]) {
                         next_use[flat[f].i] = f;
                         next_use[flat[f].j] = f;
                     }
-                std::vector<int> cand(loc2log);
+                std::vector<int> cand(ch.loc2log);
                 std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) {
                     if (next_use[a] != next_use[b]) return next_use[a] > next_use[b];
                     return a > b;
                 });
-                outgoing.assign(cand.begin(), cand.begin() + g);
-                std::sort(outgoing.begin(), outgoing.end());
+                ch.outgoing.assign(cand.begin(), cand.begin() + g);
+                std::sort(ch.outgoing.begin(), ch.outgoing.end());
+                ch.incoming = glob;
+                ch.exchange_after = true;
             }
-            if (!sub.gates.empty() || (first && sub.ztau != 0.0)) {
-                ShardOp op;
-                op.loc2log = loc2log;
-                SchedConfig cfg = cfg_in;
-                cfg.cyclic = false;
-                cfg.final_top.clear();
-                for (int q : outgoing) cfg.final_top.push_back(log2loc[q]);
-                std::vector<Segment> one{sub};
-                op.plan = compile_plan(nl, one, cfg);
-                ops.push_back(std::move(op));
-                first = false;
-            }
+            if (ch.has_work) first = false;
+            if (ch.has_work || ch.exchange_after) chunks.push_back(ch);
             if (seg_finished) break;
-            ShardOp ex;
-            ex.is_exchange = true;
-            ex.outgoing = outgoing;
-            ex.incoming = glob;
-            ops.push_back(ex);
-            glob = outgoing;  // rank bit k now carries outgoing[k]
+            glob = ch.outgoing;  // rank bit k now carries outgoing[k]
         }
         fpos += gs.size();
     }
     if (global_final) *global_final = glob;
+
+    // ---- phase B: compile the local programs back to front, so that the program before an exchange
+    // can write (with peer stores) straight into the start layout of the program after it ----
+    const int C = (int)chunks.size();
+    std::vector<ShardOp> local_ops(C);
+    std::vector<char> fused(C, 0);
+    for (int c = C - 1; c >= 0; --c) {
+        Chunk& ch = chunks[c];
+        ShardOp& op = local_ops[c];
+        op.loc2log = ch.loc2log;
+        if (!ch.has_work) continue;
+        SchedConfig cfg = cfg_in;
+        cfg.cyclic = false;
+        cfg.final_top.clear();
+        cfg.final_positions.clear();
+        cfg.next_tile_hint = 0;
+        const bool can_fuse = cfg_in.fuse_io && cfg_in.peer_exchange && ch.exchange_after && c + 1 < C && chunks[c + 1].has_work &&
+                              !local_ops[c + 1].plan.passes.empty() && !ch.sub.gates.empty();
+        if (can_fuse) {
+            const Chunk& nx = chunks[c + 1];
+            const Plan& np = local_ops[c + 1].plan;
+            cfg.final_positions.assign(nl, -1);
+            for (int l = 0; l < nl; ++l) {
+                const int q = ch.loc2log[l];
+                int k = -1;
+                for (int x = 0; x < g; ++x)
+                    if (ch.outgoing[x] == q) k = x;
+                if (k >= 0) cfg.final_positions[l] = nl + k;                  // leaves to rank bit k
+                else cfg.final_positions[l] = np.start_perm[nx.log2loc[q]];   // stays: next program's start layout
+            }
+            for (int pos = 0; pos < np.TB; ++pos) {
+                const int q = nx.loc2log[np.passes[0].tileq[pos]];
+                if (ch.log2loc[q] >= 0) cfg.next_tile_hint |= 1ull << ch.log2loc[q];
+            }
+        } else if (ch.exchange_after) {
+            for (int q : ch.outgoing) cfg.final_top.push_back(ch.log2loc[q]);
+        }
+        std::vector<Segment> one{ch.sub};
+        op.plan = compile_plan(nl, one, cfg);
+        if (can_fuse && !op.plan.passes.empty()) {
+            fused[c] = 1;
+            op.peer_last = true;
+            op.outgoing_fused = ch.outgoing;
+            op.incoming_fused = ch.incoming;
+            const Chunk& nx = chunks[c + 1];
+            const Plan& np = local_ops[c + 1].plan;
+            for (int k = 0; k < g; ++k) op.rank_out.push_back(np.start_perm[nx.log2loc[ch.incoming[k]]]);
+        }
+    }
+    std::vector<ShardOp> ops;
+    for (int c = 0; c < C; ++c) {
+        if (chunks[c].has_work) ops.push_back(std::move(local_ops[c]));
+        if (chunks[c].exchange_after && !fused[c]) {
+            ShardOp ex;
+            ex.is_exchange = true;
+            ex.outgoing = chunks[c].outgoing;
+            ex.incoming = chunks[c].incoming;
+            ops.push_back(ex);
+        }
+    }
     return ops;
 }
 
@@ -813,7 +880,13 @@ std::string sharded_to_json(const std::vector<ShardOp>& ops) {
             for (size_t i = 0; i < op.incoming.size(); ++i) os << (i ? "," : "") << op.incoming[i];
             os << "]}";
         } else {
-            os << "{\"kind\":\"local\",\"loc2log\":[";
+            os << "{\"kind\":\"local\",\"peer_last\":" << (op.peer_last ? 1 : 0) << ",\"rank_out\":[";
+            for (size_t i = 0; i < op.rank_out.size(); ++i) os << (i ? "," : "") << op.rank_out[i];
+            os << "],\"outgoing\":[";
+            for (size_t i = 0; i < op.outgoing_fused.size(); ++i) os << (i ? "," : "") << op.outgoing_fused[i];
+            os << "],\"incoming\":[";
+            for (size_t i = 0; i < op.incoming_fused.size(); ++i) os << (i ? "," : "") << op.incoming_fused[i];
+            os << "],\"loc2log\":[";
             for (size_t i = 0; i < op.loc2log.size(); ++i) os << (i ? "," : "") << op.loc2log[i];
             os << "],\"end_perm\":[";
             for (size_t i = 0; i < op.plan.end_perm.size(); ++i) os << (i ? "," : "") << op.plan.end_perm[i];

@@ -46,7 +46,7 @@ class XYKEngine:
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc: int) -> int:
-        if rc == _lib.XYK_OK or rc == _lib.XYK_NEED_EXCHANGE:
+        if rc in (_lib.XYK_OK, _lib.XYK_NEED_EXCHANGE, _lib.XYK_NEED_BARRIER):
             return rc
         msg = _lib.last_error(self._h)
         if rc == _lib.XYK_ERR_NOMEM:
@@ -197,18 +197,21 @@ def device_memory(device: int = 0) -> tuple[int, int]:
     return int(f.value), int(t.value)
 
 
-def plan_describe(K: np.ndarray, omega: np.ndarray, delta: float, order: int, reps: int, n_local: int | None = None) -> dict:
-    """Host-only: the pass program the schedule compiler emits (no GPU needed)."""
+def plan_describe(K: np.ndarray, omega: np.ndarray, delta: float, order: int, reps: int, n_local: int | None = None,
+                  peer_exchange: bool = False) -> dict:
+    """Host-only: the pass program the schedule compiler emits (no GPU needed).  With ``n_local < n`` the
+    sharded program (local programs separated by / fused with exchanges) is returned."""
     lib = _lib.load()
     K = np.ascontiguousarray(K, dtype=np.float64)
     omega = np.ascontiguousarray(omega, dtype=np.float64)
     n = omega.shape[0]
     nl = n if n_local is None else n_local
-    need = lib.xyk_plan_describe(nl, 0, _dptr(K), _dptr(omega), n, float(delta), order, reps, None, 0)
+    flag = 2 if peer_exchange else 0
+    need = lib.xyk_plan_describe(nl, flag, _dptr(K), _dptr(omega), n, float(delta), order, reps, None, 0)
     if need < 0:
         raise RuntimeError(_lib.last_error(None))
     buf = ctypes.create_string_buffer(int(need))
-    lib.xyk_plan_describe(nl, 0, _dptr(K), _dptr(omega), n, float(delta), order, reps, buf, need)
+    lib.xyk_plan_describe(nl, flag, _dptr(K), _dptr(omega), n, float(delta), order, reps, buf, need)
     return json.loads(buf.value.decode())
 
 

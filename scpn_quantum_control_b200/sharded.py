@@ -38,7 +38,7 @@ class _DevicePtr:
 class ShardedXYKEngine:
     """One rank's view of a sharded statevector; every rank must call the same methods in the same order."""
 
-    def __init__(self, n: int, *, device: int, group=None):
+    def __init__(self, n: int, *, device: int, group=None, peer_exchange: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -61,6 +61,27 @@ class ShardedXYKEngine:
         self.exchange_seconds = 0.0
         self.exchange_bytes = 0
         self.exchange_log: list[float] = []  # milliseconds per exchange
+        self.barriers = 0
+        if peer_exchange:
+            self._map_peer_buffers()
+
+    def _map_peer_buffers(self) -> None:
+        """Exchange CUDA IPC handles of both state buffers so that a pass can store into any rank."""
+        import ctypes
+
+        dist = self._dist
+        lib, h = self.eng._lib, self.eng._h
+        mine = []
+        for which in (0, 1):
+            buf = ctypes.create_string_buffer(64)
+            self.eng._check(lib.xyk_ipc_export(h, which, buf))
+            mine.append(buf.raw)
+        everyone = [None] * self.world_size
+        dist.all_gather_object(everyone, mine, group=self.group)
+        for r in range(self.world_size):
+            for which in (0, 1):
+                self.eng._check(lib.xyk_ipc_import(h, r, which, everyone[r][which]))
+        dist.barrier(group=self.group)
 
     def close(self) -> None:
         self.eng.close()
@@ -89,8 +110,12 @@ class ShardedXYKEngine:
 
     def _drive(self, rc: int) -> None:
         lib, h = self.eng._lib, self.eng._h
-        while rc == _lib.XYK_NEED_EXCHANGE:
-            self._exchange()
+        while rc in (_lib.XYK_NEED_EXCHANGE, _lib.XYK_NEED_BARRIER):
+            if rc == _lib.XYK_NEED_EXCHANGE:
+                self._exchange()
+            else:  # fence around a pass that stores into the peers' buffers (the engine has synced its stream)
+                self._dist.barrier(group=self.group)
+                self.barriers += 1
             rc = self.eng._check(lib.xyk_continue(h))
 
     # -- problem / evolution ------------------------------------------------------------------------
@@ -176,5 +201,6 @@ class ShardedXYKEngine:
 
     def stats(self) -> dict:
         st = self.eng.stats()
-        st.update(exchanges=self.exchanges, exchange_seconds=self.exchange_seconds, exchange_bytes=self.exchange_bytes)
+        st.update(exchanges=self.exchanges, exchange_seconds=self.exchange_seconds, exchange_bytes=self.exchange_bytes,
+                  barriers=self.barriers, fused_exchanges=self.barriers // 2)
         return st
