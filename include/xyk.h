@@ -156,6 +156,8 @@ typedef struct {
     int32_t timing_enabled;
     double pass_kernel_ms;   /* sum of per-launch CUDA-event durations of the fused tile pass kernel */
     int64_t pass_kernel_timed; /* number of launches in that sum (timing enabled only)            */
+    double peer_pass_ms;     /* of which: passes whose store is the fused exchange (peer stores)     */
+    int64_t peer_passes;
 } xyk_stats;
 int xyk_get_stats(xyk_handle h, xyk_stats *out);
 int xyk_enable_timing(xyk_handle h, int on);

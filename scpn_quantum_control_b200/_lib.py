@@ -43,6 +43,8 @@ class XYKStats(ctypes.Structure):
         ("timing_enabled", c_int32),
         ("pass_kernel_ms", c_double),
         ("pass_kernel_timed", c_int64),
+        ("peer_pass_ms", c_double),
+        ("peer_passes", c_int64),
     ]
 
 

@@ -605,6 +605,12 @@ int run_shard_steps(xyk_handle h) {
                 h->shard_phase = 2;
                 return XYK_NEED_BARRIER;  // every rank's stores have landed
             }
+            if (h->stats.timing_enabled && P >= 1 && h->pass_events.size() >= 2 * P) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, h->pass_events[2 * (P - 1)], h->pass_events[2 * (P - 1) + 1]);
+                h->stats.peer_pass_ms += ms;
+                h->stats.peer_passes++;
+            }
             int rc = end_program(h, prog, P);
             if (rc) return rc;
             h->shard_phase = 0;

@@ -73,6 +73,7 @@ struct Plan {
     double trailing_ztau = 0.0;    // diagonal phase after the last pass (0 if none)
     bool has_trailing_phase = false;
     int total_gates = 0, total_rounds = 0, layers1_equiv = 0;
+    uint64_t first_tile_mask = 0, last_tile_mask = 0, last_rlast_mask = 0;  // over plan indices
 };
 
 struct SchedConfig {
@@ -87,6 +88,8 @@ struct SchedConfig {
     std::vector<int> final_top;  // non-cyclic: qubits that must end on the highest physical bits, in this order
     // open programs chained across an exchange that is fused into the last pass's store:
     uint64_t next_tile_hint = 0;        // qubits (local indices) of the NEXT program's first tile that are local here
+    uint64_t prev_tile_hint = 0;        // qubits (local indices) of the PREVIOUS program's last tile that are local here
+    uint64_t prev_rlast_hint = 0;       // ... and those its last round holds in registers
     std::vector<int> final_positions;   // explicit output bit of every local index after the last pass
                                         // (>= nq: the qubit leaves to rank bit (position - nq))
 };

@@ -425,11 +425,12 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             continue;
         }
         const int pm = prev_index(p);
-        const uint64_t shared_prev = pm < 0 ? 0 : (rp.tmask & raw[pm].tmask);
-        const uint64_t rl_prev = pm < 0 ? 0 : rlast[pm];
+        const bool hinted = pm < 0 && !cfg.cyclic && cfg.prev_tile_hint;
+        const uint64_t shared_prev = pm < 0 ? (hinted ? (rp.tmask & cfg.prev_tile_hint) : 0) : (rp.tmask & raw[pm].tmask);
+        const uint64_t rl_prev = pm < 0 ? (hinted ? cfg.prev_rlast_hint : 0) : rlast[pm];
         const int budget = popc(shared_prev) - c_lane - popc(rl_prev & shared_prev);
         RawRound best;
-        if (cfg.fuse_io && pm >= 0 && budget >= 0) search_round(rp, g, cdone[p], false, shared_prev, budget, rl_prev, best);
+        if (cfg.fuse_io && (pm >= 0 || hinted) && budget >= 0) search_round(rp, g, cdone[p], false, shared_prev, budget, rl_prev, best);
         if (best.cidx.empty()) search_round(rp, g, cdone[p], false, 0, 99, rl_prev, best);
         if (best.cidx.empty()) throw std::runtime_error("compile_plan: first-round search made no progress");
         for (int c : best.cidx) cdone[p][c] = 1;
@@ -455,8 +456,9 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     auto make_layout = [&](int p, std::vector<int>& perm, int& nshared, int& nfree) {
         const uint64_t tile = raw[p].tmask;
         const int pm = prev_index(p);
-        const uint64_t prev = pm < 0 ? 0 : raw[pm].tmask;
-        const uint64_t rl_prev = pm < 0 ? 0 : rlast[pm];
+        const bool hinted = pm < 0 && !cfg.cyclic && cfg.prev_tile_hint;
+        const uint64_t prev = pm < 0 ? (hinted ? cfg.prev_tile_hint : 0) : raw[pm].tmask;
+        const uint64_t rl_prev = pm < 0 ? (hinted ? cfg.prev_rlast_hint : 0) : rlast[pm];
         perm.assign(nq, -1);
         int pos = 0;
         const uint64_t shared = tile & prev;
@@ -528,6 +530,12 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             for (int q : cfg.final_top) plan.start_perm[q] = pos++;
         }
         plan.end_perm = plan.start_perm;
+    }
+
+    if (P > 0) {
+        plan.first_tile_mask = raw[0].tmask;
+        plan.last_tile_mask = raw[P - 1].tmask;
+        plan.last_rlast_mask = rlast[P - 1];
     }
 
     // ---- 4. emit passes ----
@@ -810,48 +818,89 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
     const int C = (int)chunks.size();
     std::vector<ShardOp> local_ops(C);
     std::vector<char> fused(C, 0);
+    // how each program was chained to its successor (needed when it is recompiled in step (2))
+    std::vector<uint64_t> nop_next_hint(C, 0);
+    std::vector<std::vector<int>> nop_final_positions(C), nop_final_top(C);
+    // translate a mask over chunk a's local indices into chunk b's local indices (qubits local in both)
+    auto translate = [&](uint64_t mask, const Chunk& a, const Chunk& b) -> uint64_t {
+        uint64_t out = 0;
+        for (int l = 0; l < nl; ++l)
+            if ((mask >> l) & 1) {
+                const int lb = b.log2loc[a.loc2log[l]];
+                if (lb >= 0) out |= 1ull << lb;
+            }
+        return out;
+    };
+    auto base_cfg = [&]() {
+        SchedConfig cfg = cfg_in;
+        cfg.cyclic = false;
+        cfg.final_top.clear();
+        cfg.final_positions.clear();
+        cfg.next_tile_hint = cfg.prev_tile_hint = cfg.prev_rlast_hint = 0;
+        return cfg;
+    };
     for (int c = C - 1; c >= 0; --c) {
         Chunk& ch = chunks[c];
         ShardOp& op = local_ops[c];
         op.loc2log = ch.loc2log;
         if (!ch.has_work) continue;
-        SchedConfig cfg = cfg_in;
-        cfg.cyclic = false;
-        cfg.final_top.clear();
-        cfg.final_positions.clear();
-        cfg.next_tile_hint = 0;
-        const bool can_fuse = cfg_in.fuse_io && cfg_in.peer_exchange && ch.exchange_after && c + 1 < C && chunks[c + 1].has_work &&
-                              !local_ops[c + 1].plan.passes.empty() && !ch.sub.gates.empty();
-        if (can_fuse) {
-            const Chunk& nx = chunks[c + 1];
-            const Plan& np = local_ops[c + 1].plan;
-            cfg.final_positions.assign(nl, -1);
-            for (int l = 0; l < nl; ++l) {
-                const int q = ch.loc2log[l];
-                int k = -1;
-                for (int x = 0; x < g; ++x)
-                    if (ch.outgoing[x] == q) k = x;
-                if (k >= 0) cfg.final_positions[l] = nl + k;                  // leaves to rank bit k
-                else cfg.final_positions[l] = np.start_perm[nx.log2loc[q]];   // stays: next program's start layout
-            }
-            for (int pos = 0; pos < np.TB; ++pos) {
-                const int q = nx.loc2log[np.passes[0].tileq[pos]];
-                if (ch.log2loc[q] >= 0) cfg.next_tile_hint |= 1ull << ch.log2loc[q];
-            }
-        } else if (ch.exchange_after) {
-            for (int q : ch.outgoing) cfg.final_top.push_back(ch.log2loc[q]);
-        }
+        const bool can_fuse = cfg_in.fuse_io && cfg_in.peer_exchange && ch.exchange_after && c + 1 < C &&
+                              chunks[c + 1].has_work && !local_ops[c + 1].plan.passes.empty() && !ch.sub.gates.empty();
         std::vector<Segment> one{ch.sub};
-        op.plan = compile_plan(nl, one, cfg);
-        if (can_fuse && !op.plan.passes.empty()) {
-            fused[c] = 1;
-            op.peer_last = true;
-            op.outgoing_fused = ch.outgoing;
-            op.incoming_fused = ch.incoming;
-            const Chunk& nx = chunks[c + 1];
-            const Plan& np = local_ops[c + 1].plan;
-            for (int k = 0; k < g; ++k) op.rank_out.push_back(np.start_perm[nx.log2loc[ch.incoming[k]]]);
+        if (!can_fuse) {
+            SchedConfig cfg = base_cfg();
+            if (ch.exchange_after)
+                for (int q : ch.outgoing) cfg.final_top.push_back(ch.log2loc[q]);
+            nop_final_top[c] = cfg.final_top;
+            op.plan = compile_plan(nl, one, cfg);
+            continue;
         }
+        Chunk& nx = chunks[c + 1];
+        ShardOp& nop = local_ops[c + 1];
+        // (1) this program with the sharing hint towards the next program's first tile (learn its last tile)
+        SchedConfig cfg = base_cfg();
+        cfg.next_tile_hint = translate(nop.plan.first_tile_mask, nx, ch);
+        for (int q : ch.outgoing) cfg.final_top.push_back(ch.log2loc[q]);
+        Plan probe = compile_plan(nl, one, cfg);
+        if (probe.passes.empty()) {
+            op.plan = std::move(probe);
+            continue;
+        }
+        // (2) the next program again, now ordering its start layout around what this program leaves low
+        {
+            SchedConfig ncfg = base_cfg();
+            ncfg.prev_tile_hint = translate(probe.last_tile_mask, ch, nx);
+            ncfg.prev_rlast_hint = translate(probe.last_rlast_mask, ch, nx);
+            // keep whatever chained the next program to ITS successor
+            ncfg.next_tile_hint = nop_next_hint[c + 1];
+            ncfg.final_positions = nop_final_positions[c + 1];
+            ncfg.final_top = nop_final_top[c + 1];
+            std::vector<Segment> nseg{nx.sub};
+            nop.plan = compile_plan(nl, nseg, ncfg);
+            if (nop.peer_last) {  // its own fused exchange data is unchanged (depends on the plan after it)
+            }
+        }
+        // (3) this program for real: its last pass writes the next program's start layout
+        cfg.final_top.clear();
+        cfg.final_positions.assign(nl, -1);
+        for (int l = 0; l < nl; ++l) {
+            const int q = ch.loc2log[l];
+            int k = -1;
+            for (int x = 0; x < g; ++x)
+                if (ch.outgoing[x] == q) k = x;
+            if (k >= 0) cfg.final_positions[l] = nl + k;                        // leaves to rank bit k
+            else cfg.final_positions[l] = nop.plan.start_perm[nx.log2loc[q]];   // stays: next program's start layout
+        }
+        nop_next_hint[c] = cfg.next_tile_hint;
+        nop_final_positions[c] = cfg.final_positions;
+        op.plan = compile_plan(nl, one, cfg);
+        if (op.plan.passes.empty()) continue;
+        fused[c] = 1;
+        op.peer_last = true;
+        op.outgoing_fused = ch.outgoing;
+        op.incoming_fused = ch.incoming;
+        op.rank_out.clear();
+        for (int k = 0; k < g; ++k) op.rank_out.push_back(nop.plan.start_perm[nx.log2loc[ch.incoming[k]]]);
     }
     std::vector<ShardOp> ops;
     for (int c = 0; c < C; ++c) {

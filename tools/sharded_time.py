@@ -19,6 +19,7 @@ eng = ShardedXYKEngine(n, device=lr)
 eng.set_problem(K, w)
 eng.init_product_state()
 eng.apply_layers(0.02, 1, 1)
+eng.eng.enable_timing(True)
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.perf_counter()
 for _ in range(layers):
@@ -32,5 +33,5 @@ if rank == 0:
     print(json.dumps({"n": n, "world": world, "ms_per_layer": 1e3 * dt, "passes_last": st["last_passes"], "rounds_last": st["last_rounds"],
                       "exchanges_total": st["exchanges"], "exchange_s_total": st["exchange_seconds"],
                       "exchange_GBps": st["exchange_bytes"] / max(st["exchange_seconds"], 1e-9) / 1e9,
-                      "sweeps_total": st["state_sweeps"], "exchange_ms": [round(x, 1) for x in eng.exchange_log], "R": R, "R_ms": 1e3 * (t2 - t1), "norm2": nrm}))
+                      "sweeps_total": st["state_sweeps"], "pass_ms_mean": st["pass_kernel_ms"] / max(1, st["pass_kernel_timed"]), "peer_pass_ms_mean": st["peer_pass_ms"] / max(1, st["peer_passes"]), "peer_passes": st["peer_passes"], "passes_timed": st["pass_kernel_timed"], "exchange_ms": [round(x, 1) for x in eng.exchange_log], "R": R, "R_ms": 1e3 * (t2 - t1), "norm2": nrm}))
 eng.close(); dist.destroy_process_group()
