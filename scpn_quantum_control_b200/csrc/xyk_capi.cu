@@ -256,6 +256,9 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
     d.nq = plan.nq;
     d.nrounds = (int)pp.rounds.size();
     d.flags = (pp.fuse_load ? kPassFuseLoad : 0u) | (pp.fuse_store ? kPassFuseStore : 0u);
+    // L2 prefetch of the CTA's next tile: issued when the last round starts (measured on B200: earlier
+    // prefetches are partly evicted again and cost up to 35 % extra DRAM reads)
+    d.flags |= kPassPfLate;
     for (int b = 0; b + kTB < plan.nq; ++b) d.hi_out[b] = (uint8_t)pp.out_of_in[kTB + b];
     // tile bits ordered by their output position (unfused store)
     int order[kTB];
@@ -266,8 +269,9 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
         d.st_odst[m] = (uint8_t)pp.out_of_in[order[m]];
     }
     const PlanRound& last = pp.rounds.back();
-    for (int b = 0; b < Desc::NT; ++b) d.last_thr_out[b] = (uint8_t)pp.out_of_in[last.thrpos[b]];
-    for (int k = 0; k < kRB; ++k) d.last_reg_out[k] = (uint8_t)pp.out_of_in[last.regpos[k]];
+    const int last_nreg = last.split ? kRB + 1 : kRB;
+    for (int b = 0; b < kTB - last_nreg; ++b) d.last_thr_out[b] = (uint8_t)pp.out_of_in[last.thrpos[b]];
+    for (int k = 0; k < last_nreg; ++k) d.last_reg_out[k] = (uint8_t)pp.out_of_in[last.regpos[k]];
     // fused diagonal phase: weights per INPUT physical bit, register table of round 0
     if (pp.has_phase && h->fuse_phase && !h->zterms.empty()) {
         d.flags |= kPassHasPhase;
@@ -291,17 +295,7 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
             d.ph_reg[j] = make_double2(std::cos(pp.ztau * ph), std::sin(pp.ztau * ph));
         }
     }
-    if (h->debug_mode == 2) {  // timing experiment: pure permuting copy through round 0 only
-        d.nrounds = 1;
-        for (int b = 0; b < Desc::NT; ++b) d.last_thr_out[b] = (uint8_t)pp.out_of_in[pp.rounds[0].thrpos[b]];
-        for (int k = 0; k < kRB; ++k) d.last_reg_out[k] = (uint8_t)pp.out_of_in[pp.rounds[0].regpos[k]];
-    }
-    std::vector<PlanRound> rounds_used(pp.rounds);
-    if (h->debug_mode == 3 && pp.rounds.size() >= 2) {  // timing experiment: first + last round only, no gates
-        rounds_used = {pp.rounds.front(), pp.rounds.back()};
-        rounds_used[0].cta_sync_after = 1;
-        d.nrounds = 2;
-    }
+    const std::vector<PlanRound>& rounds_used = pp.rounds;
     lift_ok = true;
     for (int r = 0; r < d.nrounds; ++r) {
         const PlanRound& pr = rounds_used[r];
@@ -314,16 +308,18 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
     for (int r = 0; r < d.nrounds; ++r) {
         const PlanRound& pr = rounds_used[r];
         Desc::Round& R = d.rounds[r];
-        for (int b = 0; b < Desc::NT; ++b) R.thrpos[b] = (uint8_t)pr.thrpos[b];
-        for (int k = 0; k < kRB; ++k) {
+        const int nreg = pr.split ? kRB + 1 : kRB;
+        R.split = (uint16_t)(pr.split ? 1 : 0);
+        for (int b = 0; b < kTB - nreg; ++b) R.thrpos[b] = (uint8_t)pr.thrpos[b];
+        for (int k = 0; k < nreg; ++k) {
             R.regpos[k] = (uint8_t)pr.regpos[k];
             const uint32_t x = 1u << pr.regpos[k];
             uint32_t sw = x;
             if (pr.regpos[k] >= 3) sw ^= (uint32_t)swizzle_vec(pr.regpos[k]);
             R.regsw[k] = (uint16_t)sw;
         }
-        R.mask = h->debug_mode ? 0u : pr.mask;
-        R.cta_sync = (uint32_t)pr.cta_sync_after;
+        R.mask = pr.mask;
+        R.cta_sync = (uint16_t)pr.cta_sync_after;
         for (int s = 0; s < Desc::NSLOT; ++s) {
             if (!((pr.mask >> s) & 1u)) continue;
             const double phi = std::remainder(pr.phi[s], 2.0 * M_PI);
@@ -336,6 +332,14 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
             }
         }
     }
+}
+
+// tuning experiments (environment overrides of the schedule compiler's defaults)
+void apply_env(SchedConfig& cfg) {
+    if (const char* e = std::getenv("XYK_LANE_BITS")) cfg.lane_bits = std::atoi(e);
+    if (const char* e = std::getenv("XYK_NEED_SHARED")) cfg.need_shared = std::atoi(e);
+    if (const char* e = std::getenv("XYK_SPLIT")) cfg.split_rounds = std::atoi(e) != 0;
+    if (const char* e = std::getenv("XYK_SPLIT_MARGIN")) cfg.split_margin = std::atoi(e);
 }
 
 void finish_program(xyk_handle h, Program& prog) {
@@ -363,8 +367,7 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
     cfg.TB = kTB;
     cfg.RB = kRB;
     cfg.max_rounds = kMaxRounds;
-    if (const char* e = std::getenv("XYK_LANE_BITS")) cfg.lane_bits = std::atoi(e);      // tuning experiments
-    if (const char* e = std::getenv("XYK_NEED_SHARED")) cfg.need_shared = std::atoi(e);
+    apply_env(cfg);
     prog->plan = compile_plan(h->nlocal, segs, cfg);
     prog->plan.layers1_equiv = l1;
     prog->loc2log.resize(h->nlocal);
@@ -429,7 +432,19 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
             }
             cudaEventRecord(h->pass_events[2 * p], h->stream);
         }
-        if (peer) {
+        static const int ablate = std::getenv("XYK_ABLATE") ? std::atoi(std::getenv("XYK_ABLATE")) : 0;  // timing experiments only (wrong results)
+        if (ablate) {
+            auto d = prog.descs[p];
+            if (ablate & 1) for (int r = 0; r < d.nrounds; ++r) d.rounds[r].mask = 0;
+            if (ablate & 2) d.nrounds = 1;
+            if (ablate & 4) d.flags &= ~kPassHasPhase;
+            if (ablate & 16) d.flags |= kPassNoPrefetch;
+            if (ablate & 32) d.flags |= kPassPfLate;
+            if (ablate & 64) d.flags |= kPassPfEvictLast;
+            if (ablate & 128) d.flags |= kPassPlainLd;
+            if (ablate & 8) for (int r = 0; r < d.nrounds; ++r) d.rounds[r].cta_sync = 0;
+            tile_pass_kernel<kTB, kRB, true, 3, false><<<grid, nthr, smem, h->stream>>>(in, out, d, ntiles, peers);
+        } else if (peer) {
             if (prog.lift[p]) tile_pass_kernel<kTB, kRB, true, 3, true><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
             else tile_pass_kernel<kTB, kRB, false, 3, true><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
         } else {
@@ -464,6 +479,13 @@ int end_program(xyk_handle h, Program& prog, size_t timed_passes) {
             cudaEventElapsedTime(&ms, h->pass_events[2 * p], h->pass_events[2 * p + 1]);
             h->stats.pass_kernel_ms += ms;
             h->stats.pass_kernel_timed++;
+            static const bool dbg = std::getenv("XYK_DEBUG_PASSES") != nullptr;
+            if (dbg && p < plan.passes.size()) {
+                const PlanPass& pp = plan.passes[p];
+                std::fprintf(stderr, "pass %2zu: shared=%d fuse_load=%d fuse_store=%d rounds=%zu gates=%d lift=%d  %.3f ms  %.0f GB/s\n", p, pp.n_shared,
+                             (int)pp.fuse_load, (int)pp.fuse_store, pp.rounds.size(), pp.ngates, (int)prog.lift[p], ms,
+                             32.0 * (double)(1ull << h->nlocal) / (ms * 1e-3) / 1e9);
+            }
         }
     }
     XYK_CUDA(h, cudaGetLastError());
@@ -641,6 +663,7 @@ int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1) {
     cfg.RB = kRB;
     cfg.max_rounds = kMaxRounds;
     cfg.peer_exchange = h->peers_ready && h->peer_exchange_opt;
+    apply_env(cfg);
     std::vector<ShardOp> ops;
     try {
         ops = compile_sharded(h->n, current_globals(h), segs, cfg, nullptr);
@@ -1224,6 +1247,7 @@ int64_t xyk_plan_describe(int n_local, int dtype, const double* K, const double*
         cfg.TB = kTB;
         cfg.RB = kRB;
         cfg.max_rounds = kMaxRounds;
+        apply_env(cfg);
         std::string js;
         if (n_local < n) {  // sharded program: the g highest logical qubits start on the rank bits
             std::vector<int> glob;

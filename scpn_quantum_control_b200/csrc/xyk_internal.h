@@ -41,14 +41,27 @@ void build_terms(int n, const double* K, const double* omega, std::vector<PairTe
 std::vector<Segment> build_sequence(const std::vector<PairTerm>& pairs, double delta, int order,
                                     int reps, int* layers1_equiv);
 
+// Two kinds of register rounds:
+//  * complex round: each thread holds 2^RB complex amplitudes (RB register qubits) and may apply any of
+//    the RB(RB-1)/2 pairs among them;
+//  * split round: a pair rotation only mixes Re(a) with Im(b) and Im(a) with Re(b).  When every gate of a
+//    round joins a qubit of a "left" group with a qubit of a "right" group, the parity f of the right-group
+//    bits labels two independent real half-states {Re a : f(a)=h} u {Im a : f(a)!=h}, h = 0, 1.  A thread
+//    then holds ONE real component of 2^(RB+1) amplitudes in the same registers: RB+1 register qubits,
+//    (RB+1)/2 on each side, 9 gates per round for RB = 5 where a complex round reaches only 6 on such a
+//    bipartite gate set.  Thread bit 0 selects the half h.
 struct PlanRound {
-    int regq[8];      // logical qubit of register bit k (ascending for forward sweeps, descending for reverse)
+    int regq[8];      // logical qubit of register bit k (ascending for forward sweeps, descending for reverse);
+                      // split rounds: left group on bits [0, nreg/2), right group on bits [nreg/2, nreg)
     int regpos[8];    // tile-local position of register bit k
-    int thrpos[16];   // tile-local position of thread bit b (TB - RB entries)
-    uint32_t mask;    // enabled pair slots, slot order = lexicographic (a, b), a < b over register bits
+    int thrpos[16];   // tile-local position of thread-qubit bit b (TB - nreg entries; split rounds: thread bit b + 1)
+    uint32_t mask;    // enabled pair slots; complex: slot order = lexicographic (a, b), a < b over register bits;
+                      // split: slot = (nreg/2) * a + b, a = index in the left group, b = index in the right group
     double phi[16];   // angle per slot (only enabled slots are meaningful)
     int ngates;
     int cta_sync_after;  // 1: block-wide barrier after this round's exchange, 0: the data stays inside each warp
+    int split;        // 1: split round
+    int nreg;         // register qubits of this round (RB, or RB + 1 for split rounds)
 };
 
 struct PlanPass {
@@ -83,6 +96,9 @@ struct SchedConfig {
     int max_rounds = 14;   // rounds a single pass descriptor can carry
     int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
+    bool split_rounds = true;  // allow split rounds (RB + 1 register qubits over two real half-states)
+    int split_margin = 1;      // a split round must run at least this many more gates than the best complex round
+                               // (it moves the same bytes with twice as many shared-memory instructions)
     bool cyclic = true;    // the program ends in its own start layout (it can be replayed back to back)
     bool peer_exchange = false;  // sharded: fuse exchanges into the preceding pass (needs mapped peer buffers)
     std::vector<int> final_top;  // non-cyclic: qubits that must end on the highest physical bits, in this order

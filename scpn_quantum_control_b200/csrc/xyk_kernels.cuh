@@ -384,17 +384,22 @@ constexpr int kMaxRounds = 14;
 constexpr uint32_t kPassFuseLoad = 1u;   // round 0 reads its amplitudes straight from global memory
 constexpr uint32_t kPassFuseStore = 2u;  // the last round writes its amplitudes straight to global memory
 constexpr uint32_t kPassHasPhase = 4u;   // diagonal phase folded into round 0
+constexpr uint32_t kPassNoPrefetch = 8u; // do not pull the next tile into L2 ahead of time
+constexpr uint32_t kPassPfLate = 16u;     // experiment: prefetch the next tile at the start of the LAST round
+constexpr uint32_t kPassPfEvictLast = 32u; // experiment: prefetch with an L2 evict_last policy
+constexpr uint32_t kPassPlainLd = 64u;    // experiment: plain ld.global instead of ld.global.cs
 
 template <int TB, int RB>
 struct PassDesc {
     static constexpr int NT = TB - RB;
     static constexpr int NSLOT = RB * (RB - 1) / 2;
     struct Round {
-        uint8_t thrpos[8];   // tile-local position of thread bit b (NT used)
-        uint8_t regpos[8];   // tile-local position of register bit k (RB used)
+        uint8_t thrpos[8];   // tile-local position of thread bit b (NT used); split rounds: of thread bit b + 1 (NT - 1 used)
+        uint8_t regpos[8];   // tile-local position of register bit k (RB used; split rounds: RB + 1)
         uint16_t regsw[8];   // swizzled shared-memory slot offset of register bit k
         uint32_t mask;       // enabled pair slots
-        uint32_t cta_sync;   // 1: block-wide barrier after this round's exchange; 0: warp-level barrier suffices
+        uint16_t cta_sync;   // 1: block-wide barrier after this round's exchange; 0: warp-level barrier suffices
+        uint16_t split;      // 1: split round (RB + 1 register qubits, one real component per amplitude; see PlanRound)
         double ca[NSLOT];    // shear form: -tan(phi/2); standard form: cos(phi)
         double cb[NSLOT];    // sin(phi)
     };
@@ -405,7 +410,7 @@ struct PassDesc {
     uint8_t hi_out[kMaxQ];   // output bit of input bit TB + b (the tile-id bits)
     uint8_t st_lsrc[16];     // unfused store: tile-local position of the tile bit with the m-th smallest output bit
     uint8_t st_odst[16];     //                that output bit
-    uint8_t last_thr_out[8]; // fused store: output bit of the qubit on thread bit b of the LAST round
+    uint8_t last_thr_out[8]; // fused store: output bit of the qubit on thread bit b (split: b + 1) of the LAST round
     uint8_t last_reg_out[8]; //              output bit of the qubit on register bit k of the LAST round
     uint64_t out_base;       // peer passes: output-index contribution of this device's rank bits
     double ph_const;         // fused phase: contribution of the sharded (rank) bits, constant on this device
@@ -438,6 +443,12 @@ __device__ __forceinline__ void rotate2(double& x, double& y, double ca, double 
 __device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gptr), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2_bulk_evict_last(const void* gptr, uint32_t bytes) {
+    asm volatile(
+        "{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0;\n"
+        "cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, pol; }\n" ::"l"(gptr), "r"(bytes)
+        : "memory");
+}
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(addr));
@@ -465,40 +476,131 @@ __device__ __forceinline__ void store_out(double2* __restrict__ out, const PeerP
     }
 }
 
+// Shared-memory addresses / thread id through volatile asm: ptxas otherwise rematerialises them
+// (S2R SR_TID, S2UR SR_CgaCtaId) inside every round to save registers, which puts their latency on
+// the critical path of a kernel that runs only three warps per scheduler.
+__device__ __forceinline__ uint32_t smem_addr_once(const void* p) {
+    uint32_t a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }\n" : "=r"(a) : "l"(p));
+    return a;
+}
+__device__ __forceinline__ uint32_t tid_once() {
+    uint32_t t;
+    asm volatile("mov.u32 %0, %%tid.x;\n" : "=r"(t));
+    return t;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("{ .reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h; }\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// The per-round descriptors are copied from the kernel parameter (constant bank) into shared memory
+// once per CTA: a dynamically indexed constant load that misses costs several hundred cycles, and the
+// compiler issues it right at its first use; a shared-memory copy is fetched with explicit loads one
+// step ahead of its use (next round's header while this round stores, next gate's coefficients while
+// this gate is applied).
+// one real component (comp = 0: Re, 1: Im) of the amplitude at output index `addr`
+template <bool PEER>
+__device__ __forceinline__ void store_out_comp(double2* __restrict__ out, const PeerPtrs& peers, int nl, uint64_t addr, uint32_t comp,
+                                               double v) {
+    if constexpr (PEER) {
+        double* base = reinterpret_cast<double*>(peers.p[addr >> nl]);
+        __stcs(base + 2ull * (addr & ((1ull << nl) - 1ull)) + comp, v);
+    } else {
+        __stcs(reinterpret_cast<double*>(out) + 2ull * addr + comp, v);
+    }
+}
+// v with its sign bit XORed with `signmask` (0 or 0x80000000): a negation on the integer pipe
+__device__ __forceinline__ double flip_sign(double v, uint32_t signmask) {
+    return __hiloint2double(__double2hiint(v) ^ (int)signmask, __double2loint(v));
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
+}
+
 template <int TB, int RB, bool LIFT, int MINB, bool PEER>
 __global__ void __launch_bounds__(1 << (TB - RB), MINB)
 tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                  const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles, const __grid_constant__ PeerPtrs peers) {
-    constexpr int NT = TB - RB, NTHR = 1 << NT, NREG = 1 << RB;
+    constexpr int NT = TB - RB, NTHR = 1 << NT, NREG = 1 << RB, NSLOT = RB * (RB - 1) / 2;
+    constexpr int RS = RB + 1, NV = 1 << RS, HS = RS / 2;  // split rounds: register qubits, reals per thread, group size
+    static_assert(RB == 5, "round header packs six register-bit offsets; split rounds need an even RB + 1");
+    static_assert(HS * HS <= NSLOT, "split-round slots share the coefficient table");
     using Round = typename PassDesc<TB, RB>::Round;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint16_t base_tab[kMaxRounds][NTHR];  // swizzled byte offset (>>4 <<4) of each thread's base slot per round
-    const uint32_t tile_u32 = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    __shared__ uint16_t base_tab[kMaxRounds][NTHR];                      // swizzled byte offset of each thread's base slot per round
+    __shared__ __align__(16) uint4 hdr_tab[kMaxRounds + 1];              // {rb0|rb1<<16, rb2|rb3<<16, rb4|rb5<<16, mask|sync<<16|split<<17}
+    const uint32_t tile_u32 = smem_addr_once(smem_raw);
+    const uint32_t hdr_u32 = smem_addr_once(hdr_tab);
     double2* tile = reinterpret_cast<double2*>(smem_raw);
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = tid_once();
+    const uint32_t base_u32 = smem_addr_once(base_tab) + 2u * tid;
     const uint32_t flags = P.flags;
     const int nr = P.nrounds;
+    const uint32_t half = tid & 1u;   // split rounds: which real half-state this thread holds
+    const uint32_t tq = tid >> 1;     // split rounds: thread-qubit bits
+    const bool first_split = P.rounds[0].split != 0, last_split = P.rounds[nr - 1].split != 0;
 
     // per-thread constants: shared-memory base slot of every round (tile independent)
     for (int r = 0; r < nr; ++r) {
         uint32_t lin = 0;
+        if (P.rounds[r].split) {
+#pragma unroll
+            for (int b = 0; b < NT - 1; ++b)
+                if ((tq >> b) & 1u) lin |= 1u << P.rounds[r].thrpos[b];
+            base_tab[r][tid] = (uint16_t)((swz<TB>(lin) << 4) | (half << 3));
+        } else {
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+                if ((tid >> b) & 1u) lin |= 1u << P.rounds[r].thrpos[b];
+            base_tab[r][tid] = (uint16_t)(swz<TB>(lin) << 4);  // 2^TB * 16 B = 64 KiB: fits 16 bits
+        }
+    }
+    for (int r = tid; r < nr; r += NTHR) {
+        const Round& R = P.rounds[r];
+        uint4 h;
+        h.x = ((uint32_t)R.regsw[0] << 4) | ((uint32_t)R.regsw[1] << 20);
+        h.y = ((uint32_t)R.regsw[2] << 4) | ((uint32_t)R.regsw[3] << 20);
+        h.z = ((uint32_t)R.regsw[4] << 4) | ((uint32_t)R.regsw[5] << 20);
+        h.w = (R.mask & 0xffffu) | ((uint32_t)(R.cta_sync ? 1u : 0u) << 16) | ((uint32_t)(R.split ? 1u : 0u) << 17);
+        hdr_tab[r] = h;
+    }
+    // fused global load: unswizzled round-0 index of this thread (complex amplitudes)
+    uint32_t lin0 = 0;
+    if (first_split) {
+#pragma unroll
+        for (int b = 0; b < NT - 1; ++b)
+            if ((tq >> b) & 1u) lin0 |= 1u << P.rounds[0].thrpos[b];
+    } else {
 #pragma unroll
         for (int b = 0; b < NT; ++b)
-            if ((tid >> b) & 1u) lin |= 1u << P.rounds[r].thrpos[b];
-        base_tab[r][tid] = (uint16_t)(swz<TB>(lin) << 4);  // 2^TB * 16 B = 64 KiB: fits 16 bits
+            if ((tid >> b) & 1u) lin0 |= 1u << P.rounds[0].thrpos[b];
     }
-    uint32_t lin0 = 0;  // unswizzled round-0 index (fused global load)
-#pragma unroll
-    for (int b = 0; b < NT; ++b)
-        if ((tid >> b) & 1u) lin0 |= 1u << P.rounds[0].thrpos[b];
     // per-thread constants of the (unfused) load and store phases
     const uint32_t ld_slot = swz<TB>(tid);  // index bits [0, NT) <- thread id
     uint32_t st_l = 0;
     uint64_t st_d = 0;
     if (flags & kPassFuseStore) {
+        if (last_split) {
 #pragma unroll
-        for (int b = 0; b < NT; ++b)
-            if ((tid >> b) & 1u) st_d |= 1ull << P.last_thr_out[b];
+            for (int b = 0; b < NT - 1; ++b)
+                if ((tq >> b) & 1u) st_d |= 1ull << P.last_thr_out[b];
+        } else {
+#pragma unroll
+            for (int b = 0; b < NT; ++b)
+                if ((tid >> b) & 1u) st_d |= 1ull << P.last_thr_out[b];
+        }
     } else {
 #pragma unroll
         for (int b = 0; b < NT; ++b)
@@ -508,7 +610,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             }
         st_l = swz<TB>(st_l);
     }
-    // fused phase: contribution of this thread's round-0 index bits
+    // fused phase: contribution of this thread's round-0 index bits (round 0 of a phase pass is a complex round)
     double ph_thr = P.ph_const;
     if (flags & kPassHasPhase) {
 #pragma unroll
@@ -517,38 +619,72 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             ph_thr += ((tid >> b) & 1u) ? -wv : wv;
         }
     }
-    __syncthreads();  // base_tab visible (each thread only reads its own column, but keep it simple)
+    // split rounds: the odd half sees every rotation with the opposite angle; equivalently it keeps the
+    // Im-role elements (f = 1) negated and uses the same coefficients (which must stay warp-uniform)
+    const uint32_t smask = half << 31;
+    __syncthreads();  // tables visible
 
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const double2* src = in + (t << TB);
-        // pull the next tile of this CTA into L2 while this one is being processed
-        if (tid == 0 && t + gridDim.x < ntiles) prefetch_l2_bulk(in + ((t + gridDim.x) << TB), (uint32_t)(sizeof(double2) << TB));
+        auto prefetch_next = [&]() {
+            if (tid == 0 && !(flags & kPassNoPrefetch) && t + gridDim.x < ntiles) {
+                if (flags & kPassPfEvictLast) prefetch_l2_bulk_evict_last(in + ((t + gridDim.x) << TB), (uint32_t)(sizeof(double2) << TB));
+                else prefetch_l2_bulk(in + ((t + gridDim.x) << TB), (uint32_t)(sizeof(double2) << TB));
+            }
+        };
+        if (!(flags & kPassPfLate)) prefetch_next();
         uint64_t obase = P.out_base;
         for (int b = 0; b < P.nq - TB; ++b)
             if ((t >> b) & 1ull) obase |= 1ull << P.hi_out[b];
-        uint32_t base_next = base_tab[0][tid];
+        uint4 hdr = lds_u4(hdr_u32);
+        uint32_t boff = lds_u16(base_u32);
 
         for (int r = 0; r < nr; ++r) {
-            const Round& R = P.rounds[r];
-            const uint32_t boff = base_next;                    // byte offset of this thread's base slot in the tile
-            if (r + 1 < nr) base_next = base_tab[r + 1][tid];   // off the critical path of the next round
-            uint32_t rb[RB];
-#pragma unroll
-            for (int k = 0; k < RB; ++k) rb[k] = (uint32_t)R.regsw[k] << 4;
-            double2 a[NREG];
+            uint32_t rb[RS];
+            rb[0] = hdr.x & 0xffffu;
+            rb[1] = hdr.x >> 16;
+            rb[2] = hdr.y & 0xffffu;
+            rb[3] = hdr.y >> 16;
+            rb[4] = hdr.z & 0xffffu;
+            rb[5] = hdr.z >> 16;
+            const bool split = (hdr.w >> 17) & 1u;
+            if ((flags & kPassPfLate) && r == nr - 1) prefetch_next();
+            const Round& R = P.rounds[r];  // gate coefficients stay in the constant bank: a uniform operand of DFMA
+                                           // (measured: DFMA with three vector-register sources issues ~15 % slower)
+            // complex round: v[2j], v[2j+1] = Re, Im of register index j (RB bits);
+            // split round:   v[j] = one real component of register index j (RB + 1 bits)
+            double v[NV];
 
-            if (r == 0) {
-                if (flags & kPassFuseLoad) {
+            // ---------------- load ----------------
+            if (r == 0 && (flags & kPassFuseLoad)) {
+                if (split) {
+                    const double* p0 = reinterpret_cast<const double*>(src + lin0) + half;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        uint32_t off = 0;
+#pragma unroll
+                        for (int k = 0; k < RS; ++k)
+                            if ((j >> k) & 1) off += 2u << P.rounds[0].regpos[k];
+                        // component: Re if f(j) == half, f = parity of the right-group bits
+                        const int fj = __builtin_popcount(j >> HS) & 1;
+                        v[j] = __ldcs(fj ? p0 + off + 1 - 2 * (int)half : p0 + off);
+                        if (fj) v[j] = flip_sign(v[j], smask);
+                    }
+                } else {
                     const double2* p0 = src + lin0;
 #pragma unroll
                     for (int j = 0; j < NREG; ++j) {
                         uint32_t off = 0;
 #pragma unroll
                         for (int k = 0; k < RB; ++k)
-                            if ((j >> k) & 1) off += 1u << R.regpos[k];
-                        a[j] = __ldcs(p0 + off);
+                            if ((j >> k) & 1) off += 1u << P.rounds[0].regpos[k];
+                        const double2 a = (flags & kPassPlainLd) ? p0[off] : __ldcs(p0 + off);
+                        v[2 * j] = a.x;
+                        v[2 * j + 1] = a.y;
                     }
-                } else {
+                }
+            } else {
+                if (r == 0) {
                     __syncthreads();  // every warp is done reading the previous tile out of shared memory
 #pragma unroll
                     for (int k = 0; k < NREG; ++k) {
@@ -557,85 +693,143 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     }
                     cp_async_wait_all();
                     __syncthreads();
+                }
+                if (split) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        uint32_t off = (__builtin_popcount(j >> HS) & 1) ? 8u : 0u;
+#pragma unroll
+                        for (int k = 0; k < RS; ++k)
+                            if ((j >> k) & 1) off ^= rb[k];
+                        v[j] = lds64(tile_u32 + (boff ^ off));
+                        if (__builtin_popcount(j >> HS) & 1) v[j] = flip_sign(v[j], smask);
+                    }
+                } else {
 #pragma unroll
                     for (int j = 0; j < NREG; ++j) {
                         uint32_t off = 0;
 #pragma unroll
                         for (int k = 0; k < RB; ++k)
                             if ((j >> k) & 1) off ^= rb[k];
-                        a[j] = lds128(tile_u32 + (boff ^ off));
+                        const double2 a = lds128(tile_u32 + (boff ^ off));
+                        v[2 * j] = a.x;
+                        v[2 * j + 1] = a.y;
                     }
                 }
-                if (flags & kPassHasPhase) {
-                    double ph = ph_thr;
-                    for (int b = 0; b < P.nq - TB; ++b) {
-                        const double wv = P.ph_w[TB + b];
-                        ph += ((t >> b) & 1ull) ? -wv : wv;
-                    }
-                    double sn, cs;
-                    sincos(P.ph_tau * ph, &sn, &cs);
+            }
+
+            // ---------------- diagonal phase (complex round 0 only) ----------------
+            if (r == 0 && (flags & kPassHasPhase)) {
+                double ph = ph_thr;
+                for (int b = 0; b < P.nq - TB; ++b) {
+                    const double wv = P.ph_w[TB + b];
+                    ph += ((t >> b) & 1ull) ? -wv : wv;
+                }
+                double sn, cs;
+                sincos(P.ph_tau * ph, &sn, &cs);
 #pragma unroll
-                    for (int j = 0; j < NREG; ++j) {
-                        const double2 f = P.ph_reg[j];
-                        const double fr = cs * f.x - sn * f.y, fi = cs * f.y + sn * f.x;
-                        const double xr = a[j].x, xi = a[j].y;
-                        a[j].x = xr * fr - xi * fi;
-                        a[j].y = xr * fi + xi * fr;
+                for (int j = 0; j < NREG; ++j) {
+                    const double2 f = P.ph_reg[j];
+                    const double fr = cs * f.x - sn * f.y, fi = cs * f.y + sn * f.x;
+                    const double xr = v[2 * j], xi = v[2 * j + 1];
+                    v[2 * j] = xr * fr - xi * fi;
+                    v[2 * j + 1] = xr * fi + xi * fr;
+                }
+            }
+
+            // ---------------- gates ----------------
+            const uint32_t mask = hdr.w & 0xffffu;
+            if (split) {
+#pragma unroll
+                for (int x = 0; x < HS; ++x) {
+#pragma unroll
+                    for (int y = HS; y < RS; ++y) {
+                        const int slot = HS * x + (y - HS);
+                        if (mask & (1u << slot)) {
+                            const double ca = R.ca[slot], cb = R.cb[slot];
+#pragma unroll
+                            for (int m = 0; m < NV / 4; ++m) {
+                                const int j0 = insert_zero(insert_zero(m, x), y);
+                                const int jA = j0 | (1 << x), jB = j0 | (1 << y);
+                                // half 0 holds Re(A), Im(B) when f(jA) = 0 and Im(A), Re(B) otherwise (roles swap)
+                                if (__builtin_popcount(jA >> HS) & 1) rotate2<LIFT>(v[jB], v[jA], ca, cb);
+                                else rotate2<LIFT>(v[jA], v[jB], ca, cb);
+                            }
+                        }
                     }
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < NREG; ++j) {
-                    uint32_t off = 0;
+                for (int x = 0; x < RB; ++x) {
 #pragma unroll
-                    for (int k = 0; k < RB; ++k)
-                        if ((j >> k) & 1) off ^= rb[k];
-                    a[j] = lds128(tile_u32 + (boff ^ off));
-                }
-            }
-
-            const uint32_t mask = R.mask;
+                    for (int y = x + 1; y < RB; ++y) {
+                        const int slot = x * RB - x * (x + 1) / 2 + (y - x - 1);
+                        if (mask & (1u << slot)) {
+                            const double ca = R.ca[slot], cb = R.cb[slot];
 #pragma unroll
-            for (int x = 0; x < RB; ++x) {
-#pragma unroll
-                for (int y = x + 1; y < RB; ++y) {
-                    const int slot = x * RB - x * (x + 1) / 2 + (y - x - 1);
-                    if (mask & (1u << slot)) {
-                        const double ca = R.ca[slot], cb = R.cb[slot];
-#pragma unroll
-                        for (int m = 0; m < NREG / 4; ++m) {
-                            const int j0 = insert_zero(insert_zero(m, x), y);
-                            const int jA = j0 | (1 << x), jB = j0 | (1 << y);
-                            rotate2<LIFT>(a[jA].x, a[jB].y, ca, cb);
-                            rotate2<LIFT>(a[jB].x, a[jA].y, ca, cb);
+                            for (int m = 0; m < NREG / 4; ++m) {
+                                const int j0 = insert_zero(insert_zero(m, x), y);
+                                const int jA = j0 | (1 << x), jB = j0 | (1 << y);
+                                rotate2<LIFT>(v[2 * jA], v[2 * jB + 1], ca, cb);
+                                rotate2<LIFT>(v[2 * jB], v[2 * jA + 1], ca, cb);
+                            }
                         }
                     }
                 }
             }
 
+            // ---------------- store / exchange ----------------
             if (r == nr - 1 && (flags & kPassFuseStore)) {
                 const uint64_t dbase = obase + st_d;
+                if (split) {
 #pragma unroll
-                for (int j = 0; j < NREG; ++j) {
-                    uint64_t off = 0;
+                    for (int j = 0; j < NV; ++j) {
+                        uint64_t off = 0;
 #pragma unroll
-                    for (int k = 0; k < RB; ++k)
-                        if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
-                    store_out<PEER>(out, peers, P.nq, dbase + off, a[j]);
+                        for (int k = 0; k < RS; ++k)
+                            if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
+                        const uint32_t fj = __builtin_popcount(j >> HS) & 1;
+                        store_out_comp<PEER>(out, peers, P.nq, dbase + off, fj ^ half, fj ? flip_sign(v[j], smask) : v[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NREG; ++j) {
+                        uint64_t off = 0;
+#pragma unroll
+                        for (int k = 0; k < RB; ++k)
+                            if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
+                        store_out<PEER>(out, peers, P.nq, dbase + off, make_double2(v[2 * j], v[2 * j + 1]));
+                    }
                 }
             } else {
+                // next round's header and base slot: issued ahead of the stores, back before the barrier
+                const uint4 hdr_next = lds_u4(hdr_u32 + (uint32_t)(r + 1) * 16u);
+                const uint32_t boff_next = lds_u16(base_u32 + (uint32_t)(r + 1) * (uint32_t)(NTHR * 2));
                 // tile boundary: the previous tile's last round (other warps) must be done reading
                 if (r == 0 && (flags & kPassFuseLoad)) __syncthreads();
+                if (split) {
 #pragma unroll
-                for (int j = 0; j < NREG; ++j) {
-                    uint32_t off = 0;
+                    for (int j = 0; j < NV; ++j) {
+                        uint32_t off = (__builtin_popcount(j >> HS) & 1) ? 8u : 0u;
 #pragma unroll
-                    for (int k = 0; k < RB; ++k)
-                        if ((j >> k) & 1) off ^= rb[k];
-                    sts128(tile_u32 + (boff ^ off), a[j]);
+                        for (int k = 0; k < RS; ++k)
+                            if ((j >> k) & 1) off ^= rb[k];
+                        sts64(tile_u32 + (boff ^ off), (__builtin_popcount(j >> HS) & 1) ? flip_sign(v[j], smask) : v[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NREG; ++j) {
+                        uint32_t off = 0;
+#pragma unroll
+                        for (int k = 0; k < RB; ++k)
+                            if ((j >> k) & 1) off ^= rb[k];
+                        sts128(tile_u32 + (boff ^ off), make_double2(v[2 * j], v[2 * j + 1]));
+                    }
                 }
-                if (R.cta_sync) __syncthreads();
+                if ((hdr.w >> 16) & 1u) __syncthreads();
                 else __syncwarp();
+                hdr = hdr_next;
+                boff = boff_next;
             }
         }
 

@@ -331,7 +331,11 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         uint64_t rmask = 0;
         std::vector<int> cidx;  // indices into the pass's gate_idx
         bool reverse = false;
+        bool split = false;     // split round: gates only between lmask and rmask & ~lmask
+        uint64_t lmask = 0;
     };
+    const int RS = RB + 1;  // register qubits of a split round
+    const bool can_split = cfg.split_rounds && (RS % 2 == 0) && TB - RS >= 3 && RS <= 8;
     std::vector<std::vector<RawRound>> rr(P);
     std::vector<uint64_t> rlast(P, 0), rfirst(P, 0);
     const int c_lane = std::min(cfg.lane_bits, TB);
@@ -357,7 +361,81 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     };
     // exhaustive search over RB-subsets of the tile; `limit_mask`/`limit` cap |R & limit_mask|;
     // `prefer` breaks ties towards subsets overlapping it (keeps the union with a neighbour small)
-    auto search_round = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cdone,
+    // split-round closure: a gate runs iff it joins the left group with the right group
+    auto split_closure = [&](const std::vector<Gate>& g, const std::vector<int>& cand, const std::vector<char>& cdone,
+                             uint64_t lm, uint64_t rm, bool reverse_scan, std::vector<int>& out) {
+        out.clear();
+        uint64_t blocked = 0;
+        int sweep = -1;
+        const uint64_t both = lm | rm;
+        const int nc = (int)cand.size();
+        for (int cc = 0; cc < nc; ++cc) {
+            const int c = reverse_scan ? nc - 1 - cc : cc;
+            if (cdone[c]) continue;
+            const Gate& q = g[cand[c]];
+            const uint64_t bi = 1ull << q.i, bj = 1ull << q.j, m = bi | bj;
+            const bool cross = ((bi & lm) && (bj & rm)) || ((bi & rm) && (bj & lm));
+            const bool fits = cross && !(m & blocked) && (sweep < 0 || q.sweep == sweep);
+            if (fits) {
+                out.push_back(c);
+                sweep = q.sweep;
+            } else {
+                blocked |= m;
+            }
+            if (popc(both & ~blocked) < 2) break;
+        }
+    };
+    auto search_split = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cdone, bool reverse_scan,
+                            uint64_t limit_mask, int limit, uint64_t prefer, RawRound& best) {
+        std::vector<int> tq;
+        for (int q = 0; q < nq; ++q)
+            if ((rp.tmask >> q) & 1) tq.push_back(q);
+        const int tn = (int)tq.size();
+        best.rmask = 0;
+        best.lmask = 0;
+        best.cidx.clear();
+        best.split = true;
+        if (tn < RS) return;
+        const int H = RS / 2;
+        std::vector<int> idx(RS), sub(H), ex;
+        for (int k = 0; k < RS; ++k) idx[k] = k;
+        int best_pref = -1;
+        while (true) {
+            uint64_t sm = 0;
+            for (int k = 0; k < RS; ++k) sm |= 1ull << tq[idx[k]];
+            if (popc(sm & limit_mask) <= limit) {
+                // left groups containing the smallest element (the mirrored split runs the same gates)
+                for (int k = 0; k < H; ++k) sub[k] = k;
+                while (true) {
+                    uint64_t lm = 0;
+                    for (int k = 0; k < H; ++k) lm |= 1ull << tq[idx[sub[k]]];
+                    split_closure(g, rp.gate_idx, cdone, lm, sm & ~lm, reverse_scan, ex);
+                    const int pref = popc(sm & prefer);
+                    if (ex.size() > best.cidx.size() || (ex.size() == best.cidx.size() && !ex.empty() && pref > best_pref)) {
+                        best.cidx = ex;
+                        best.rmask = sm;
+                        best.lmask = lm;
+                        best_pref = pref;
+                    }
+                    int k = H - 1;
+                    while (k >= 1 && sub[k] == RS - H + k) --k;
+                    if (k < 1) break;  // sub[0] stays 0
+                    ++sub[k];
+                    for (int m = k + 1; m < H; ++m) sub[m] = sub[m - 1] + 1;
+                }
+            }
+            int k = RS - 1;
+            while (k >= 0 && idx[k] == tn - RS + k) --k;
+            if (k < 0) break;
+            ++idx[k];
+            for (int m = k + 1; m < RS; ++m) idx[m] = idx[m - 1] + 1;
+        }
+        if (!best.cidx.empty()) {
+            best.reverse = g[rp.gate_idx[best.cidx[0]]].reverse;
+            std::sort(best.cidx.begin(), best.cidx.end());
+        }
+    };
+    auto search_complex = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cdone,
                             bool reverse_scan, uint64_t limit_mask, int limit, uint64_t prefer, RawRound& best) {
         std::vector<int> tq;
         for (int q = 0; q < nq; ++q)
@@ -392,6 +470,17 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             std::sort(best.cidx.begin(), best.cidx.end());
         }
     };
+    // the better of a complex round and (when allowed) a split round; ties go to the complex round
+    // (half as many shared-memory instructions for the same bytes)
+    bool allow_split = can_split;
+    auto search_round = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cdone,
+                            bool reverse_scan, uint64_t limit_mask, int limit, uint64_t prefer, RawRound& best) {
+        search_complex(rp, g, cdone, reverse_scan, limit_mask, limit, prefer, best);
+        if (!allow_split) return;
+        RawRound sp;
+        search_split(rp, g, cdone, reverse_scan, limit_mask, limit, prefer, sp);
+        if ((int)sp.cidx.size() >= (int)best.cidx.size() + cfg.split_margin) best = sp;
+    };
 
     std::vector<std::vector<char>> cdone(P);
     std::vector<RawRound> last_round(P), first_round(P);
@@ -410,6 +499,14 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         }
         if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
         if (best.cidx.empty()) throw std::runtime_error("compile_plan: last-round search made no progress");
+        if (best.split && best.cidx.size() == rp.gate_idx.size() && rp.has_phase) {
+            // a single round that also carries the diagonal phase must hold whole complex amplitudes
+            allow_split = false;
+            best = RawRound();
+            if (cfg.fuse_io && s - c_lane >= 1) search_round(rp, g, cdone[p], true, shared_next, (s - c_lane + 1) / 2, 0, best);
+            if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
+            allow_split = can_split;
+        }
         for (int c : best.cidx) cdone[p][c] = 1;
         rlast[p] = best.rmask;
         last_round[p] = best;
@@ -430,8 +527,10 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         const uint64_t rl_prev = pm < 0 ? (hinted ? cfg.prev_rlast_hint : 0) : rlast[pm];
         const int budget = popc(shared_prev) - c_lane - popc(rl_prev & shared_prev);
         RawRound best;
+        allow_split = can_split && !rp.has_phase;  // the fused phase multiplies whole complex amplitudes
         if (cfg.fuse_io && (pm >= 0 || hinted) && budget >= 0) search_round(rp, g, cdone[p], false, shared_prev, budget, rl_prev, best);
         if (best.cidx.empty()) search_round(rp, g, cdone[p], false, 0, 99, rl_prev, best);
+        allow_split = can_split;
         if (best.cidx.empty()) throw std::runtime_error("compile_plan: first-round search made no progress");
         for (int c : best.cidx) cdone[p][c] = 1;
         ndone += best.cidx.size();
@@ -620,10 +719,25 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             PlanRound pr;
             std::memset(&pr, 0, sizeof(pr));
             std::vector<int> rq;
-            for (int q = 0; q < nq; ++q)
-                if ((R.rmask >> q) & 1) rq.push_back(q);
-            if (R.reverse) std::reverse(rq.begin(), rq.end());
-            for (int k = 0; k < RB; ++k) {
+            const int nreg = R.split ? RS : RB;
+            pr.split = R.split ? 1 : 0;
+            pr.nreg = nreg;
+            if (R.split) {
+                std::vector<int> lq, rgt;
+                for (int q = 0; q < nq; ++q)
+                    if ((R.rmask >> q) & 1) (((R.lmask >> q) & 1) ? lq : rgt).push_back(q);
+                if (R.reverse) {
+                    std::reverse(lq.begin(), lq.end());
+                    std::reverse(rgt.begin(), rgt.end());
+                }
+                rq = lq;
+                rq.insert(rq.end(), rgt.begin(), rgt.end());
+            } else {
+                for (int q = 0; q < nq; ++q)
+                    if ((R.rmask >> q) & 1) rq.push_back(q);
+                if (R.reverse) std::reverse(rq.begin(), rq.end());
+            }
+            for (int k = 0; k < nreg; ++k) {
                 pr.regq[k] = rq[k];
                 pr.regpos[k] = qpos[rq[k]];
             }
@@ -631,7 +745,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             std::vector<int> lanepos, warppos;
             for (int pos = 0; pos < TB; ++pos) {
                 bool isreg = false;
-                for (int k = 0; k < RB; ++k) isreg |= (pr.regpos[k] == pos);
+                for (int k = 0; k < nreg; ++k) isreg |= (pr.regpos[k] == pos);
                 if (isreg) continue;
                 if ((wsel[r] >> inv[pos]) & 1) warppos.push_back(pos);
                 else lanepos.push_back(pos);
@@ -675,15 +789,20 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             for (int c : R.cidx) {
                 const Gate& q = g[rp.gate_idx[c]];
                 int a = -1, b = -1;
-                for (int k = 0; k < RB; ++k) {
+                for (int k = 0; k < nreg; ++k) {
                     if (pr.regq[k] == q.i || pr.regq[k] == q.j) {
                         if (a < 0) a = k;
                         else b = k;
                     }
                 }
                 int slot = 0;
-                for (int x = 0; x < a; ++x) slot += RB - 1 - x;
-                slot += b - a - 1;
+                if (R.split) {
+                    if (a < 0 || b < RS / 2 || a >= RS / 2) throw std::runtime_error("compile_plan: split round gate inside one group");
+                    slot = (RS / 2) * a + (b - RS / 2);
+                } else {
+                    for (int x = 0; x < a; ++x) slot += RB - 1 - x;
+                    slot += b - a - 1;
+                }
                 if ((pr.mask >> slot) & 1u) throw std::runtime_error("compile_plan: pair scheduled twice in one round");
                 pr.mask |= 1u << slot;
                 pr.phi[slot] = gop[rp.gate_idx[c]].phi;
@@ -966,22 +1085,33 @@ std::string plan_to_json(const Plan& plan) {
            << ",\"fuse_store\":" << (pp.fuse_store ? 1 : 0) << ",\"rounds\":[";
         for (size_t r = 0; r < pp.rounds.size(); ++r) {
             const PlanRound& pr = pp.rounds[r];
-            os << (r ? "," : "") << "{\"regq\":[";
-            for (int k = 0; k < plan.RB; ++k) os << (k ? "," : "") << pr.regq[k];
+            const int nreg = pr.nreg ? pr.nreg : plan.RB;
+            os << (r ? "," : "") << "{\"split\":" << pr.split << ",\"regq\":[";
+            for (int k = 0; k < nreg; ++k) os << (k ? "," : "") << pr.regq[k];
             os << "],\"regpos\":[";
-            for (int k = 0; k < plan.RB; ++k) os << (k ? "," : "") << pr.regpos[k];
+            for (int k = 0; k < nreg; ++k) os << (k ? "," : "") << pr.regpos[k];
             os << "],\"thrpos\":[";
-            for (int k = 0; k < plan.TB - plan.RB; ++k) os << (k ? "," : "") << pr.thrpos[k];
+            for (int k = 0; k < plan.TB - nreg; ++k) os << (k ? "," : "") << pr.thrpos[k];
             os << "],\"mask\":" << pr.mask << ",\"cta_sync_after\":" << pr.cta_sync_after << ",\"gates\":[";
             bool firstg = true;
-            int slot = 0;
-            for (int a = 0; a < plan.RB; ++a)
-                for (int b = a + 1; b < plan.RB; ++b, ++slot)
-                    if ((pr.mask >> slot) & 1) {
-                        os << (firstg ? "" : ",") << "[" << pr.regq[a] << "," << pr.regq[b] << ","
-                           << pr.phi[slot] << "]";
-                        firstg = false;
-                    }
+            if (pr.split) {
+                const int H = nreg / 2;
+                for (int a = 0; a < H; ++a)
+                    for (int b = 0; b < H; ++b)
+                        if ((pr.mask >> (H * a + b)) & 1) {
+                            os << (firstg ? "" : ",") << "[" << pr.regq[a] << "," << pr.regq[H + b] << "," << pr.phi[H * a + b] << "]";
+                            firstg = false;
+                        }
+            } else {
+                int slot = 0;
+                for (int a = 0; a < plan.RB; ++a)
+                    for (int b = a + 1; b < plan.RB; ++b, ++slot)
+                        if ((pr.mask >> slot) & 1) {
+                            os << (firstg ? "" : ",") << "[" << pr.regq[a] << "," << pr.regq[b] << ","
+                               << pr.phi[slot] << "]";
+                            firstg = false;
+                        }
+            }
             os << "]}";
         }
         os << "]}";
