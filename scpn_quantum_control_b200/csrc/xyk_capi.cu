@@ -313,10 +313,7 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
         for (int b = 0; b < kTB - nreg; ++b) R.thrpos[b] = (uint8_t)pr.thrpos[b];
         for (int k = 0; k < nreg; ++k) {
             R.regpos[k] = (uint8_t)pr.regpos[k];
-            const uint32_t x = 1u << pr.regpos[k];
-            uint32_t sw = x;
-            if (pr.regpos[k] >= 3) sw ^= (uint32_t)swizzle_vec(pr.regpos[k]);
-            R.regsw[k] = (uint16_t)sw;
+            R.regsw[k] = (uint16_t)(16u * pad_slot(1u << pr.regpos[k]));
         }
         R.mask = pr.mask;
         R.cta_sync = (uint16_t)pr.cta_sync_after;
@@ -379,7 +376,7 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
 }
 
 int configure_pass_kernels(xyk_handle h) {
-    const int smem = (1 << kTB) * 16;
+    const int smem = (int)tile_bytes<kTB>();
     XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, true, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -410,7 +407,7 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
     const Plan& plan = prog.plan;
     const uint64_t ntiles = 1ull << (h->nlocal - kTB);
     const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)h->pass_grid);
-    const int smem = (1 << kTB) * 16;
+    const int smem = (int)tile_bytes<kTB>();
     const int nthr = 1 << (kTB - kRB);
     PeerPtrs peers{};
     if (peer)
@@ -442,6 +439,7 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
             if (ablate & 32) d.flags |= kPassPfLate;
             if (ablate & 64) d.flags |= kPassPfEvictLast;
             if (ablate & 128) d.flags |= kPassPlainLd;
+            if (ablate & 256) d.flags |= kPassStagger;
             if (ablate & 8) for (int r = 0; r < d.nrounds; ++r) d.rounds[r].cta_sync = 0;
             tile_pass_kernel<kTB, kRB, true, 3, false><<<grid, nthr, smem, h->stream>>>(in, out, d, ntiles, peers);
         } else if (peer) {

@@ -113,11 +113,10 @@ struct SchedConfig {
 // Compile the segments into tile passes over nq local qubits.  Throws std::runtime_error.
 Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& cfg);
 
-// GF(2)^3 swizzle vector of tile-local position p (positions 0..2 are the identity part).
-inline int swizzle_vec(int p) {
-    static const int V[16] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6, 7, 1, 2};
-    return V[p];
-}
+// Bank class of tile-local position p in the padded shared-memory tile layout (xyk_kernels.cuh,
+// pad_slot): the 16-byte-column stride of position p is 1, 2 or 4 (mod 8) for p mod 3 = 0, 1, 2.
+// Three lane bits on positions of three different classes are bank-conflict free.
+inline int lane_class(int p) { return p % 3; }
 
 std::string plan_to_json(const Plan& plan);
 

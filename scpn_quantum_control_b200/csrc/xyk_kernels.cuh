@@ -25,23 +25,17 @@ template <> struct cplx<float> { using type = float2; };
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ constexpr uint32_t swz_mask(int bit, int nbits) {
-    // positions p >= 3 whose swizzle vector has `bit` set
-    uint32_t m = 0;
-    constexpr int V[16] = {1, 2, 4, 3, 5, 6, 7, 1, 2, 4, 3, 5, 6, 7, 1, 2};
-    for (int p = 3; p < nbits; ++p)
-        if ((V[p] >> bit) & 1) m |= 1u << p;
-    return m;
-}
-
-// tile-local index -> shared-memory slot: the low three bits (16-byte column inside a 128-byte
-// bank window) are XORed with a GF(2)-linear function of the higher bits, so that any three
-// index bits with independent swizzle vectors spread eight lanes over eight distinct columns.
+// tile-local index -> shared-memory slot (16-byte units) of the padded tile layout:
+//     slot(x) = x + (x >> 3) + (x >> 6) + (x >> 9)
+// The map is ADDITIVE over the index bits (slot(x) = sum of slot(1 << p) over the set bits p), so an
+// address is "per-thread base + warp-uniform offset" and needs no per-access vector arithmetic
+// (LDS [R + UR]), and the strides slot(1 << p) mod 8 run 1, 2, 4, 1, 2, 4, ...: any three lane bits on
+// positions with three different p mod 3 spread eight lanes over the eight 16-byte columns of a
+// 128-byte bank window (conflict free).  Cost: 14 % more shared memory than a dense tile.
+__host__ __device__ constexpr uint32_t pad_slot(uint32_t x) { return x + (x >> 3) + (x >> 6) + (x >> 9); }
 template <int TB>
-__device__ __forceinline__ uint32_t swz(uint32_t x) {
-    constexpr uint32_t M0 = swz_mask(0, TB), M1 = swz_mask(1, TB), M2 = swz_mask(2, TB);
-    const uint32_t s = (__popc(x & M0) & 1u) | ((__popc(x & M1) & 1u) << 1) | ((__popc(x & M2) & 1u) << 2);
-    return x ^ s;
+constexpr uint32_t tile_bytes() {
+    return (pad_slot((1u << TB) - 1u) + 1u) * 16u;
 }
 
 __host__ __device__ constexpr int insert_zero(int v, int pos) {
@@ -388,6 +382,7 @@ constexpr uint32_t kPassNoPrefetch = 8u; // do not pull the next tile into L2 ah
 constexpr uint32_t kPassPfLate = 16u;     // experiment: prefetch the next tile at the start of the LAST round
 constexpr uint32_t kPassPfEvictLast = 32u; // experiment: prefetch with an L2 evict_last policy
 constexpr uint32_t kPassPlainLd = 64u;    // experiment: plain ld.global instead of ld.global.cs
+constexpr uint32_t kPassStagger = 128u;   // experiment: CTAs that share an SM start a third of a tile period apart
 
 template <int TB, int RB>
 struct PassDesc {
@@ -396,7 +391,7 @@ struct PassDesc {
     struct Round {
         uint8_t thrpos[8];   // tile-local position of thread bit b (NT used); split rounds: of thread bit b + 1 (NT - 1 used)
         uint8_t regpos[8];   // tile-local position of register bit k (RB used; split rounds: RB + 1)
-        uint16_t regsw[8];   // swizzled shared-memory slot offset of register bit k
+        uint16_t regsw[8];   // shared-memory byte stride of register bit k: 16 * pad_slot(1 << regpos[k])
         uint32_t mask;       // enabled pair slots
         uint16_t cta_sync;   // 1: block-wide barrier after this round's exchange; 0: warp-level barrier suffices
         uint16_t split;      // 1: split round (RB + 1 register qubits, one real component per amplitude; see PlanRound)
@@ -500,6 +495,27 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return v;
 }
 
+// ---- bulk asynchronous tile load (TMA, cp.async.bulk) signalled through an mbarrier ----
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+// one thread: the generic-proxy reads of the buffer are ordered before the async-proxy write, the
+// mbarrier expects `bytes`, the copy completes on it
+__device__ __forceinline__ void bulk_load_tile(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst), "l"(gsrc), "r"(bytes),
+                 "r"(mbar)
+                 : "memory");
+}
+
 // The per-round descriptors are copied from the kernel parameter (constant bank) into shared memory
 // once per CTA: a dynamically indexed constant load that misses costs several hundred cycles, and the
 // compiler issues it right at its first use; a shared-memory copy is fetched with explicit loads one
@@ -539,43 +555,50 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     static_assert(HS * HS <= NSLOT, "split-round slots share the coefficient table");
     using Round = typename PassDesc<TB, RB>::Round;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint16_t base_tab[kMaxRounds][NTHR];                      // swizzled byte offset of each thread's base slot per round
-    __shared__ __align__(16) uint4 hdr_tab[kMaxRounds + 1];              // {rb0|rb1<<16, rb2|rb3<<16, rb4|rb5<<16, mask|sync<<16|split<<17}
+    // per round: {rs0|rs1<<16, rs2|rs3<<16, rs4|rs5<<16, mask|sync<<16|split<<17}, {ts0|ts1<<16, ts2|ts3<<16, ts4|ts5<<16, ts6}
+    // rs = byte stride of a register bit, ts = byte stride of a thread bit
+    __shared__ __align__(16) uint4 hdr_tab[2 * (kMaxRounds + 1)];
+    __shared__ __align__(8) unsigned long long tile_mbar;
+    const uint32_t mbar_u32 = smem_addr_once(&tile_mbar);
     const uint32_t tile_u32 = smem_addr_once(smem_raw);
     const uint32_t hdr_u32 = smem_addr_once(hdr_tab);
     double2* tile = reinterpret_cast<double2*>(smem_raw);
     const uint32_t tid = tid_once();
-    const uint32_t base_u32 = smem_addr_once(base_tab) + 2u * tid;
     const uint32_t flags = P.flags;
     const int nr = P.nrounds;
     const uint32_t half = tid & 1u;   // split rounds: which real half-state this thread holds
     const uint32_t tq = tid >> 1;     // split rounds: thread-qubit bits
     const bool first_split = P.rounds[0].split != 0, last_split = P.rounds[nr - 1].split != 0;
 
-    // per-thread constants: shared-memory base slot of every round (tile independent)
-    for (int r = 0; r < nr; ++r) {
-        uint32_t lin = 0;
-        if (P.rounds[r].split) {
-#pragma unroll
-            for (int b = 0; b < NT - 1; ++b)
-                if ((tq >> b) & 1u) lin |= 1u << P.rounds[r].thrpos[b];
-            base_tab[r][tid] = (uint16_t)((swz<TB>(lin) << 4) | (half << 3));
-        } else {
-#pragma unroll
-            for (int b = 0; b < NT; ++b)
-                if ((tid >> b) & 1u) lin |= 1u << P.rounds[r].thrpos[b];
-            base_tab[r][tid] = (uint16_t)(swz<TB>(lin) << 4);  // 2^TB * 16 B = 64 KiB: fits 16 bits
-        }
-    }
     for (int r = tid; r < nr; r += NTHR) {
         const Round& R = P.rounds[r];
-        uint4 h;
-        h.x = ((uint32_t)R.regsw[0] << 4) | ((uint32_t)R.regsw[1] << 20);
-        h.y = ((uint32_t)R.regsw[2] << 4) | ((uint32_t)R.regsw[3] << 20);
-        h.z = ((uint32_t)R.regsw[4] << 4) | ((uint32_t)R.regsw[5] << 20);
+        uint4 h, g;
+        h.x = (uint32_t)R.regsw[0] | ((uint32_t)R.regsw[1] << 16);
+        h.y = (uint32_t)R.regsw[2] | ((uint32_t)R.regsw[3] << 16);
+        h.z = (uint32_t)R.regsw[4] | ((uint32_t)R.regsw[5] << 16);
         h.w = (R.mask & 0xffffu) | ((uint32_t)(R.cta_sync ? 1u : 0u) << 16) | ((uint32_t)(R.split ? 1u : 0u) << 17);
-        hdr_tab[r] = h;
+        uint32_t ts[8];
+        for (int b = 0; b < 8; ++b) ts[b] = b < (R.split ? NT - 1 : NT) ? 16u * pad_slot(1u << R.thrpos[b]) : 0u;
+        g.x = ts[0] | (ts[1] << 16);
+        g.y = ts[2] | (ts[3] << 16);
+        g.z = ts[4] | (ts[5] << 16);
+        g.w = ts[6];
+        hdr_tab[2 * r] = h;
+        hdr_tab[2 * r + 1] = g;
     }
+    // byte offset of this thread's base slot in a round: sum of the strides of its set thread bits
+    auto thread_base = [&](const uint4& g, bool split) -> uint32_t {
+        const uint32_t bits = split ? tq : tid;
+        uint32_t b = split ? (half << 3) : 0u;
+        if (bits & 1u) b += g.x & 0xffffu;
+        if (bits & 2u) b += g.x >> 16;
+        if (bits & 4u) b += g.y & 0xffffu;
+        if (bits & 8u) b += g.y >> 16;
+        if (bits & 16u) b += g.z & 0xffffu;
+        if (bits & 32u) b += g.z >> 16;
+        if (bits & 64u) b += g.w;
+        return b;
+    };
     // fused global load: unswizzled round-0 index of this thread (complex amplitudes)
     uint32_t lin0 = 0;
     if (first_split) {
@@ -588,7 +611,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             if ((tid >> b) & 1u) lin0 |= 1u << P.rounds[0].thrpos[b];
     }
     // per-thread constants of the (unfused) load and store phases
-    const uint32_t ld_slot = swz<TB>(tid);  // index bits [0, NT) <- thread id
+    const uint32_t ld_slot = pad_slot(tid);  // index bits [0, NT) <- thread id
     uint32_t st_l = 0;
     uint64_t st_d = 0;
     if (flags & kPassFuseStore) {
@@ -608,7 +631,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 st_l |= 1u << P.st_lsrc[b];
                 st_d |= 1ull << P.st_odst[b];
             }
-        st_l = swz<TB>(st_l);
+        st_l = pad_slot(st_l);
     }
     // fused phase: contribution of this thread's round-0 index bits (round 0 of a phase pass is a complex round)
     double ph_thr = P.ph_const;
@@ -622,8 +645,20 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     // split rounds: the odd half sees every rotation with the opposite angle; equivalently it keeps the
     // Im-role elements (f = 1) negated and uses the same coefficients (which must stay warp-uniform)
     const uint32_t smask = half << 31;
-    __syncthreads();  // tables visible
+    if (tid == 0) mbar_init(mbar_u32, 1);
+    __syncthreads();  // tables and mbarrier visible
 
+    // Fused load = the whole 64 KiB tile arrives by ONE bulk asynchronous copy into the (linear) front of the
+    // tile buffer; it is issued as soon as the previous tile's last round has read its data out of the
+    // buffer, so the global load overlaps that round's arithmetic and the global store.
+    constexpr uint32_t kTileLinearBytes = (uint32_t)(sizeof(double2) << TB);
+    uint32_t tile_parity = 0;
+    if ((flags & kPassFuseLoad) && tid == 0) bulk_load_tile(tile_u32, in + ((uint64_t)blockIdx.x << TB), kTileLinearBytes, mbar_u32);
+
+    if (flags & kPassStagger) {
+        const uint32_t k = blockIdx.x / ((gridDim.x + 2) / 3);
+        for (uint32_t i = 0; i < k * 5; ++i) __nanosleep(1000);
+    }
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const double2* src = in + (t << TB);
         auto prefetch_next = [&]() {
@@ -632,12 +667,12 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 else prefetch_l2_bulk(in + ((t + gridDim.x) << TB), (uint32_t)(sizeof(double2) << TB));
             }
         };
-        if (!(flags & kPassPfLate)) prefetch_next();
+        if (!(flags & (kPassPfLate | kPassFuseLoad))) prefetch_next();
         uint64_t obase = P.out_base;
         for (int b = 0; b < P.nq - TB; ++b)
             if ((t >> b) & 1ull) obase |= 1ull << P.hi_out[b];
         uint4 hdr = lds_u4(hdr_u32);
-        uint32_t boff = lds_u16(base_u32);
+        uint32_t boff = tile_u32 + thread_base(lds_u4(hdr_u32 + 16u), first_split);
 
         for (int r = 0; r < nr; ++r) {
             uint32_t rb[RS];
@@ -648,7 +683,8 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             rb[4] = hdr.z & 0xffffu;
             rb[5] = hdr.z >> 16;
             const bool split = (hdr.w >> 17) & 1u;
-            if ((flags & kPassPfLate) && r == nr - 1) prefetch_next();
+            const uint32_t boff1 = boff + 8u - (half << 4);  // split rounds: base of the elements with f(j) = 1
+            if ((flags & kPassPfLate) && !(flags & kPassFuseLoad) && r == nr - 1) prefetch_next();
             const Round& R = P.rounds[r];  // gate coefficients stay in the constant bank: a uniform operand of DFMA
                                            // (measured: DFMA with three vector-register sources issues ~15 % slower)
             // complex round: v[2j], v[2j+1] = Re, Im of register index j (RB bits);
@@ -657,28 +693,30 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 
             // ---------------- load ----------------
             if (r == 0 && (flags & kPassFuseLoad)) {
+                mbar_wait(mbar_u32, tile_parity);
+                tile_parity ^= 1u;
                 if (split) {
-                    const double* p0 = reinterpret_cast<const double*>(src + lin0) + half;
+                    const uint32_t p0 = tile_u32 + (lin0 << 4) + (half << 3);
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
                         uint32_t off = 0;
 #pragma unroll
                         for (int k = 0; k < RS; ++k)
-                            if ((j >> k) & 1) off += 2u << P.rounds[0].regpos[k];
+                            if ((j >> k) & 1) off += 16u << P.rounds[0].regpos[k];
                         // component: Re if f(j) == half, f = parity of the right-group bits
                         const int fj = __builtin_popcount(j >> HS) & 1;
-                        v[j] = __ldcs(fj ? p0 + off + 1 - 2 * (int)half : p0 + off);
+                        v[j] = lds64((fj ? p0 + 8u - (half << 4) : p0) + off);
                         if (fj) v[j] = flip_sign(v[j], smask);
                     }
                 } else {
-                    const double2* p0 = src + lin0;
+                    const uint32_t p0 = tile_u32 + (lin0 << 4);
 #pragma unroll
                     for (int j = 0; j < NREG; ++j) {
                         uint32_t off = 0;
 #pragma unroll
                         for (int k = 0; k < RB; ++k)
-                            if ((j >> k) & 1) off += 1u << P.rounds[0].regpos[k];
-                        const double2 a = (flags & kPassPlainLd) ? p0[off] : __ldcs(p0 + off);
+                            if ((j >> k) & 1) off += 16u << P.rounds[0].regpos[k];
+                        const double2 a = lds128(p0 + off);
                         v[2 * j] = a.x;
                         v[2 * j + 1] = a.y;
                     }
@@ -688,8 +726,8 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     __syncthreads();  // every warp is done reading the previous tile out of shared memory
 #pragma unroll
                     for (int k = 0; k < NREG; ++k) {
-                        const uint32_t hi = swz<TB>((uint32_t)k << NT);  // constant after unrolling
-                        cp_async16(&tile[ld_slot ^ hi], src + ((uint32_t)k << NT) + tid);
+                        const uint32_t hi = pad_slot((uint32_t)k << NT);  // constant after unrolling
+                        cp_async16(&tile[ld_slot + hi], src + ((uint32_t)k << NT) + tid);
                     }
                     cp_async_wait_all();
                     __syncthreads();
@@ -697,11 +735,12 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 if (split) {
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
-                        uint32_t off = (__builtin_popcount(j >> HS) & 1) ? 8u : 0u;
+                        uint32_t off = 0;
 #pragma unroll
                         for (int k = 0; k < RS; ++k)
-                            if ((j >> k) & 1) off ^= rb[k];
-                        v[j] = lds64(tile_u32 + (boff ^ off));
+                            if ((j >> k) & 1) off += rb[k];
+                        // component f(j) ^ half: the two per-thread bases differ by +-8 bytes
+                        v[j] = lds64(((__builtin_popcount(j >> HS) & 1) ? boff1 : boff) + off);
                         if (__builtin_popcount(j >> HS) & 1) v[j] = flip_sign(v[j], smask);
                     }
                 } else {
@@ -710,12 +749,18 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                         uint32_t off = 0;
 #pragma unroll
                         for (int k = 0; k < RB; ++k)
-                            if ((j >> k) & 1) off ^= rb[k];
-                        const double2 a = lds128(tile_u32 + (boff ^ off));
+                            if ((j >> k) & 1) off += rb[k];
+                        const double2 a = lds128(boff + off);
                         v[2 * j] = a.x;
                         v[2 * j + 1] = a.y;
                     }
                 }
+            }
+
+            // the last round holds the tile in registers: the buffer is free for the next tile
+            if ((flags & kPassFuseLoad) && (flags & kPassFuseStore) && r == nr - 1) {
+                __syncthreads();
+                if (tid == 0 && t + gridDim.x < ntiles) bulk_load_tile(tile_u32, in + ((t + gridDim.x) << TB), kTileLinearBytes, mbar_u32);
             }
 
             // ---------------- diagonal phase (complex round 0 only) ----------------
@@ -803,18 +848,19 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 }
             } else {
                 // next round's header and base slot: issued ahead of the stores, back before the barrier
-                const uint4 hdr_next = lds_u4(hdr_u32 + (uint32_t)(r + 1) * 16u);
-                const uint32_t boff_next = lds_u16(base_u32 + (uint32_t)(r + 1) * (uint32_t)(NTHR * 2));
+                const uint4 hdr_next = lds_u4(hdr_u32 + (uint32_t)(r + 1) * 32u);
+                const uint4 thr_next = lds_u4(hdr_u32 + (uint32_t)(r + 1) * 32u + 16u);
                 // tile boundary: the previous tile's last round (other warps) must be done reading
                 if (r == 0 && (flags & kPassFuseLoad)) __syncthreads();
                 if (split) {
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
-                        uint32_t off = (__builtin_popcount(j >> HS) & 1) ? 8u : 0u;
+                        uint32_t off = 0;
 #pragma unroll
                         for (int k = 0; k < RS; ++k)
-                            if ((j >> k) & 1) off ^= rb[k];
-                        sts64(tile_u32 + (boff ^ off), (__builtin_popcount(j >> HS) & 1) ? flip_sign(v[j], smask) : v[j]);
+                            if ((j >> k) & 1) off += rb[k];
+                        const bool fj = __builtin_popcount(j >> HS) & 1;
+                        sts64((fj ? boff1 : boff) + off, fj ? flip_sign(v[j], smask) : v[j]);
                     }
                 } else {
 #pragma unroll
@@ -822,14 +868,14 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                         uint32_t off = 0;
 #pragma unroll
                         for (int k = 0; k < RB; ++k)
-                            if ((j >> k) & 1) off ^= rb[k];
-                        sts128(tile_u32 + (boff ^ off), make_double2(v[2 * j], v[2 * j + 1]));
+                            if ((j >> k) & 1) off += rb[k];
+                        sts128(boff + off, make_double2(v[2 * j], v[2 * j + 1]));
                     }
                 }
                 if ((hdr.w >> 16) & 1u) __syncthreads();
                 else __syncwarp();
                 hdr = hdr_next;
-                boff = boff_next;
+                boff = tile_u32 + thread_base(thr_next, (hdr_next.w >> 17) & 1u);
             }
         }
 
@@ -846,7 +892,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                         lk |= 1u << P.st_lsrc[NT + b];
                         dk |= 1ull << P.st_odst[NT + b];
                     }
-                store_out<PEER>(out, peers, P.nq, dbase + dk, tile[st_l ^ swz<TB>(lk)]);
+                store_out<PEER>(out, peers, P.nq, dbase + dk, tile[st_l + pad_slot(lk)]);
+            }
+            if (flags & kPassFuseLoad) {
+                __syncthreads();
+                if (tid == 0 && t + gridDim.x < ntiles) bulk_load_tile(tile_u32, in + ((t + gridDim.x) << TB), kTileLinearBytes, mbar_u32);
             }
         }
     }

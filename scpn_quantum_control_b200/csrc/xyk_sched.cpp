@@ -214,6 +214,10 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     }
 
     const uint64_t all_mask = nq >= 64 ? ~0ull : ((1ull << nq) - 1);
+    // qubits of the program's first tile ranked by how late the first pass uses them: when the last tile
+    // has to share qubits with the first one (cyclic programs), the late ones are free to become the
+    // lane bits of the fused global I/O between the two passes
+    std::vector<int> first_use(nq, 1 << 30);
     auto grow_tile = [&](const std::vector<Gate>& g, const std::vector<char>& done, int first,
                          uint64_t prev, uint64_t firstTile, int need_prev, int need_first) -> uint64_t {
         uint64_t T = (1ull << g[first].i) | (1ull << g[first].j);
@@ -238,7 +242,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 closure(g, done, first, T | (1ull << q), ex);
                 const int sc = (int)ex.size();
                 const int share = (int)((prev >> q) & 1);
-                if (sc > best || (sc == best && share > bshare)) {
+                const bool later = firstTile && bq >= 0 && ((firstTile >> q) & 1) && first_use[q] > first_use[bq];
+                if (sc > best || (sc == best && share > bshare) || (sc == best && share == bshare && later)) {
                     best = sc;
                     bq = q;
                     bshare = share;
@@ -279,6 +284,14 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // cyclic closure: the last tile must share `need` qubits with the first one so that the
     // program can be replayed from its own end layout.  If it does not, peel gates off the last
     // pass(es) and re-plan them with the extra constraint.
+    if (!raw.empty()) {
+        const std::vector<Gate>& g0 = sg[raw[0].seg];
+        for (size_t k = 0; k < raw[0].gate_idx.size(); ++k) {
+            const Gate& q = g0[raw[0].gate_idx[k]];
+            first_use[q.i] = std::min(first_use[q.i], (int)k);
+            first_use[q.j] = std::min(first_use[q.j], (int)k);
+        }
+    }
     if (!cfg.cyclic) first_tile = cfg.next_tile_hint;  // open program: share with the next program's first tile
     if (first_tile && !raw.empty() && popc(raw.back().tmask & first_tile) < std::min(need, popc(first_tile)) && nq > TB) {
         const int s = raw.back().seg;
@@ -493,7 +506,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         const uint64_t shared_next = rp.tmask & next_tile(p);
         const int s = popc(shared_next);
         RawRound best;
-        if (cfg.fuse_io && s - c_lane >= 1) {
+        if (cfg.fuse_io && s - c_lane >= 0) {
             const int budget = (s - c_lane + 1) / 2;
             search_round(rp, g, cdone[p], true, shared_next, budget, 0, best);
         }
@@ -503,7 +516,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             // a single round that also carries the diagonal phase must hold whole complex amplitudes
             allow_split = false;
             best = RawRound();
-            if (cfg.fuse_io && s - c_lane >= 1) search_round(rp, g, cdone[p], true, shared_next, (s - c_lane + 1) / 2, 0, best);
+            if (cfg.fuse_io && s - c_lane >= 0) search_round(rp, g, cdone[p], true, shared_next, (s - c_lane + 1) / 2, 0, best);
             if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
             allow_split = can_split;
         }
@@ -758,15 +771,14 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 order = lanepos;  // ascending OUTPUT position: lanes 0.. write contiguous addresses
                 std::sort(order.begin(), order.end(), [&](int a, int b) { return pp.out_of_in[a] < pp.out_of_in[b]; });
             } else {
-                // three positions with linearly independent swizzle vectors first (bank-conflict free)
+                // three positions of three different bank classes first (bank-conflict free)
                 int pick[3] = {-1, -1, -1};
                 bool found = false;
                 for (int a = 0; a < nl && !found; ++a)
                     for (int b = a + 1; b < nl && !found; ++b)
                         for (int c = b + 1; c < nl && !found; ++c) {
-                            const int va = swizzle_vec(lanepos[a]), vb = swizzle_vec(lanepos[b]),
-                                      vc = swizzle_vec(lanepos[c]);
-                            if (va != vb && va != vc && vb != vc && (va ^ vb) != vc) {
+                            const int va = lane_class(lanepos[a]), vb = lane_class(lanepos[b]), vc = lane_class(lanepos[c]);
+                            if (va != vb && va != vc && vb != vc) {
                                 pick[0] = a; pick[1] = b; pick[2] = c;
                                 found = true;
                             }

@@ -192,6 +192,182 @@ __global__ void __launch_bounds__(128, 3) pass_split(const double* __restrict__ 
     }
 }
 
+// Variant of pass_split: the tile is loaded by ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier) into
+// the CTA's own tile buffer as soon as the last round has read its data out of it, i.e. the next
+// tile's global load overlaps the last round's arithmetic and the global store.
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(mbar),
+        "r"(phase)
+        : "memory");
+}
+template <int G, int ROWS = 1>
+__global__ void __launch_bounds__(128, 3) pass_split_tma(const double* __restrict__ in, double* __restrict__ out, int nb, int c, int R, double ca,
+                                                         double cb) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long mbar_storage;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&mbar_storage);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t w0 = base + warp * 16384u + lane * 8u;
+    const uint64_t ntiles = 1ull << (nb - 12);
+    const int abits = 12 - c;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint64_t t) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(65536u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(base),
+                     "l"(in + (t << 13)), "r"(65536u), "r"(mbar)
+                     : "memory");
+    };
+    auto pad = [](uint32_t x) { return x + (x >> 3) + (x >> 6) + (x >> 9); };
+    // ROWS > 1: the tile arrives as ROWS bulk copies of 65536 / ROWS bytes, each placed at its padded slot
+    auto issue_rows = [&](uint64_t t) {
+        constexpr uint32_t RB_ = 65536u / ROWS;      // bytes per copy
+        constexpr int PER = ROWS / 128 > 0 ? ROWS / 128 : 1;
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(65536u) : "memory");
+        }
+        __syncthreads();
+        if (tid * PER < ROWS) {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const uint32_t row = tid * PER + i;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                                 base + pad(row * (RB_ / 16u)) * 16u),
+                             "l"(reinterpret_cast<const char*>(in + (t << 13)) + (size_t)row * RB_), "r"(RB_), "r"(mbar)
+                             : "memory");
+            }
+        }
+    };
+    if (ROWS == 1) {
+        if (tid == 0 && blockIdx.x < ntiles) issue(blockIdx.x);
+    } else if (blockIdx.x < ntiles) issue_rows(blockIdx.x);
+    uint32_t phase = 0;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t a_ = t & ((1ull << abits) - 1), rest = t >> abits;
+        const uint64_t obase = (a_ << c) | (rest << (24 - c));
+        double a[64];
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+        // round 0 reads the linear tile: thread tid, register k -> double index k * 128 + tid (conflict free)
+        if (ROWS == 1) {
+#pragma unroll
+            for (int k = 0; k < 64; ++k) a[k] = lds64(base + (k * 128 + tid) * 8u);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 64; ++k) a[k] = lds64(base + pad((uint32_t)(k * 64)) * 16u + pad(tid >> 1) * 16u + (tid & 1) * 8u);
+        }
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int gte = 0; gte < G; ++gte) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    double& x0 = a[4 * m + 1];
+                    double& y0 = a[4 * m + 2];
+                    x0 = fma(ca, y0, x0); y0 = fma(cb, x0, y0); x0 = fma(ca, y0, x0);
+                }
+            }
+            if (r + 1 < R) {
+                if (r == 0) __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 64; ++j) sts64(w0 + j * 256, a[j]);
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 64; ++j) a[j] = lds64(w0 + ((j * 256) ^ ((r & 1) << 9)));
+                if (r + 2 == R) {  // the last round holds its data: the buffer is free for the next tile
+                    __syncthreads();
+                    if (ROWS == 1) {
+                        if (tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
+                    } else if (t + gridDim.x < ntiles) issue_rows(t + gridDim.x);
+                }
+            }
+        }
+        if (R == 1) {
+            __syncthreads();
+            if (ROWS == 1) {
+                if (tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
+            } else if (t + gridDim.x < ntiles) issue_rows(t + gridDim.x);
+        }
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const uint32_t o = (k * 128 + tid) >> 1;  // complex slot
+            const uint64_t dst = obase | (o & ((1u << c) - 1)) | ((uint64_t)(o >> c) << 12);
+            __stcs(out + 2 * dst + (tid & 1), a[k]);
+        }
+    }
+}
+
+// Variant: the next tile is staged by per-thread cp.async (LDGSTS, 16 B each, 32 per thread) into a PADDED
+// layout (arbitrary placement, no lane constraint on the first round), issued after the last round's loads.
+__global__ void __launch_bounds__(128, 3) pass_split_cpasync(const double* __restrict__ in, double* __restrict__ out, int nb, int c, int R, double ca,
+                                                             double cb) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t w0 = base + warp * 16384u + lane * 8u;
+    const uint64_t ntiles = 1ull << (nb - 12);
+    const int abits = 12 - c;
+    auto pad = [](uint32_t x) { return x + (x >> 3) + (x >> 6) + (x >> 9); };
+    const uint32_t st0 = base + pad(tid) * 16u;
+    auto issue = [&](uint64_t t) {
+        const double2* src = reinterpret_cast<const double2*>(in) + (t << 12) + tid;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(st0 + pad((uint32_t)k << 7) * 16u), "l"(src + k * 128) : "memory");
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (blockIdx.x < ntiles) issue(blockIdx.x);
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t a_ = t & ((1ull << abits) - 1), rest = t >> abits;
+        const uint64_t obase = (a_ << c) | (rest << (24 - c));
+        double a[64];
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();
+        // round 0 reads the padded tile (here: 8-byte units k * 128 + tid of the dense index, through pad())
+#pragma unroll
+        for (int k = 0; k < 64; ++k) a[k] = lds64(base + pad((uint32_t)(k * 64)) * 16u + pad(tid >> 1) * 16u + (tid & 1) * 8u);
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int gte = 0; gte < 9; ++gte) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    double& x0 = a[4 * m + 1];
+                    double& y0 = a[4 * m + 2];
+                    x0 = fma(ca, y0, x0); y0 = fma(cb, x0, y0); x0 = fma(ca, y0, x0);
+                }
+            }
+            if (r + 1 < R) {
+                if (r == 0) __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 64; ++j) sts64(w0 + j * 256, a[j]);
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 64; ++j) a[j] = lds64(w0 + ((j * 256) ^ ((r & 1) << 9)));
+                if (r + 2 == R) {
+                    __syncthreads();
+                    if (t + gridDim.x < ntiles) issue(t + gridDim.x);
+                }
+            }
+        }
+        if (R == 1) {
+            __syncthreads();
+            if (t + gridDim.x < ntiles) issue(t + gridDim.x);
+        }
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const uint32_t o = (k * 128 + tid) >> 1;
+            const uint64_t dst = obase | (o & ((1u << c) - 1)) | ((uint64_t)(o >> c) << 12);
+            __stcs(out + 2 * dst + (tid & 1), a[k]);
+        }
+    }
+}
+
 // Realism ladder for the complex round: which feature of the real kernel costs what?
 //  F & 1: runtime XOR addressing (per-thread base ^ xor-combination of five runtime register-bit offsets)
 //  F & 2: runtime gate mask (ten slot branches) with coefficients fetched from shared memory one gate ahead
@@ -438,6 +614,57 @@ int main() {
         const double gb = 2.0 * (double)(sizeof(double2) << nb) / 1e9;
         printf("split: R=%d rounds x 9 gates = %2d gates : %.3f ms per pass  %.0f GB/s (%.1f%%)\n", R, 9 * R, best, gb / (best * 1e-3),
                100.0 * gb / (best * 1e-3) / 6541.5);
+    }
+    cudaFuncSetAttribute(pass_split_tma<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    for (int R : {1, 2, 3, 4, 5, 6}) {
+        float best = 1e30f;
+        for (int it = 0; it < 3; ++it) {
+            cudaEventRecord(e0);
+            pass_split_tma<9><<<148 * 3, 128, 65536>>>((const double*)a, (double*)b, nb, 5, R, 1e-9, -1e-9);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (it > 0 && ms < best) best = ms;
+        }
+        const double gb = 2.0 * (double)(sizeof(double2) << nb) / 1e9;
+        printf("split+TMA load: R=%d rounds x 9 gates = %2d gates : %.3f ms per pass  %.0f GB/s (%.1f%%)\n", R, 9 * R, best, gb / (best * 1e-3),
+               100.0 * gb / (best * 1e-3) / 6541.5);
+    }
+    cudaFuncSetAttribute(pass_split_tma<9, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75008);
+    cudaFuncSetAttribute(pass_split_tma<9, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75008);
+    for (int rows : {512, 128})
+        for (int R : {1, 2, 4, 5, 6}) {
+            float best = 1e30f;
+            for (int it = 0; it < 3; ++it) {
+                cudaEventRecord(e0);
+                if (rows == 512) pass_split_tma<9, 512><<<148 * 3, 128, 75008>>>((const double*)a, (double*)b, nb, 5, R, 1e-9, -1e-9);
+                else pass_split_tma<9, 128><<<148 * 3, 128, 75008>>>((const double*)a, (double*)b, nb, 5, R, 1e-9, -1e-9);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (it > 0 && ms < best) best = ms;
+            }
+            const double gb = 2.0 * (double)(sizeof(double2) << nb) / 1e9;
+            printf("split+TMA %3d-row padded load: R=%d rounds x 9 gates : %.3f ms per pass  %.0f GB/s (%.1f%%)\n", rows, R, best, gb / (best * 1e-3),
+                   100.0 * gb / (best * 1e-3) / 6541.5);
+        }
+    cudaFuncSetAttribute(pass_split_cpasync, cudaFuncAttributeMaxDynamicSharedMemorySize, 75008);
+    for (int R : {1, 2, 3, 4, 5, 6}) {
+        float best = 1e30f;
+        for (int it = 0; it < 3; ++it) {
+            cudaEventRecord(e0);
+            pass_split_cpasync<<<148 * 3, 128, 75008>>>((const double*)a, (double*)b, nb, 5, R, 1e-9, -1e-9);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (it > 0 && ms < best) best = ms;
+        }
+        const double gb = 2.0 * (double)(sizeof(double2) << nb) / 1e9;
+        printf("split+cp.async padded load: R=%d rounds x 9 gates = %2d gates : %.3f ms per pass  %.0f GB/s (%.1f%%)\n", R, 9 * R, best,
+               gb / (best * 1e-3), 100.0 * gb / (best * 1e-3) / 6541.5);
     }
     cudaFuncSetAttribute(pass_shfl<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     for (int R : {1})
