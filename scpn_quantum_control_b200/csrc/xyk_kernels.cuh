@@ -732,25 +732,42 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     cp_async_wait_all();
                     __syncthreads();
                 }
+                // address = per-thread base of the high register bits (8 vector adds per burst) + warp-uniform
+                // offset of the low register bits: LDS [R + UR], no per-access vector arithmetic
                 if (split) {
+                    uint32_t bh[1 << HS], lo[1 << HS];
+#pragma unroll
+                    for (int c = 0; c < (1 << HS); ++c) {
+                        uint32_t hi = 0, l = 0;
+#pragma unroll
+                        for (int k = 0; k < HS; ++k) {
+                            if ((c >> k) & 1) hi += rb[HS + k];
+                            if ((c >> k) & 1) l += rb[k];
+                        }
+                        // component f ^ half, f = parity of the right-group (high) bits: two bases 8 bytes apart
+                        bh[c] = ((__builtin_popcount(c) & 1) ? boff1 : boff) + hi;
+                        lo[c] = l;
+                    }
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
-                        uint32_t off = 0;
-#pragma unroll
-                        for (int k = 0; k < RS; ++k)
-                            if ((j >> k) & 1) off += rb[k];
-                        // component f(j) ^ half: the two per-thread bases differ by +-8 bytes
-                        v[j] = lds64(((__builtin_popcount(j >> HS) & 1) ? boff1 : boff) + off);
+                        v[j] = lds64(bh[j >> HS] + lo[j & ((1 << HS) - 1)]);
                         if (__builtin_popcount(j >> HS) & 1) v[j] = flip_sign(v[j], smask);
                     }
                 } else {
+                    uint32_t bh[8], lo[4];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t hi = 0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if ((c >> k) & 1) hi += rb[2 + k];
+                        bh[c] = boff + hi;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) lo[c] = ((c & 1) ? rb[0] : 0u) + ((c & 2) ? rb[1] : 0u);
 #pragma unroll
                     for (int j = 0; j < NREG; ++j) {
-                        uint32_t off = 0;
-#pragma unroll
-                        for (int k = 0; k < RB; ++k)
-                            if ((j >> k) & 1) off += rb[k];
-                        const double2 a = lds128(boff + off);
+                        const double2 a = lds128(bh[j >> 2] + lo[j & 3]);
                         v[2 * j] = a.x;
                         v[2 * j + 1] = a.y;
                     }
@@ -826,24 +843,51 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             // ---------------- store / exchange ----------------
             if (r == nr - 1 && (flags & kPassFuseStore)) {
                 const uint64_t dbase = obase + st_d;
-                if (split) {
+                if constexpr (PEER) {
+                    if (split) {
 #pragma unroll
-                    for (int j = 0; j < NV; ++j) {
-                        uint64_t off = 0;
+                        for (int j = 0; j < NV; ++j) {
+                            uint64_t off = 0;
 #pragma unroll
-                        for (int k = 0; k < RS; ++k)
-                            if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
-                        const uint32_t fj = __builtin_popcount(j >> HS) & 1;
-                        store_out_comp<PEER>(out, peers, P.nq, dbase + off, fj ^ half, fj ? flip_sign(v[j], smask) : v[j]);
+                            for (int k = 0; k < RS; ++k)
+                                if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
+                            const uint32_t fj = __builtin_popcount(j >> HS) & 1;
+                            store_out_comp<PEER>(out, peers, P.nq, dbase + off, fj ^ half, fj ? flip_sign(v[j], smask) : v[j]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NREG; ++j) {
+                            uint64_t off = 0;
+#pragma unroll
+                            for (int k = 0; k < RB; ++k)
+                                if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
+                            store_out<PEER>(out, peers, P.nq, dbase + off, make_double2(v[2 * j], v[2 * j + 1]));
+                        }
                     }
                 } else {
+                    // per-thread byte pointer once per tile + warp-uniform byte offsets of the register bits
+                    char* pb = reinterpret_cast<char*>(out) + (dbase << 4);
+                    if (split) {
+                        char* pb0 = pb + (half << 3);          // elements with f = 0: component `half`
+                        char* pb1 = pb + 8 - (half << 3);      // elements with f = 1: the other component
 #pragma unroll
-                    for (int j = 0; j < NREG; ++j) {
-                        uint64_t off = 0;
+                        for (int j = 0; j < NV; ++j) {
+                            uint64_t off = 0;
 #pragma unroll
-                        for (int k = 0; k < RB; ++k)
-                            if ((j >> k) & 1) off += 1ull << P.last_reg_out[k];
-                        store_out<PEER>(out, peers, P.nq, dbase + off, make_double2(v[2 * j], v[2 * j + 1]));
+                            for (int k = 0; k < RS; ++k)
+                                if ((j >> k) & 1) off += 16ull << P.last_reg_out[k];
+                            const bool fj = __builtin_popcount(j >> HS) & 1;
+                            __stcs(reinterpret_cast<double*>((fj ? pb1 : pb0) + off), fj ? flip_sign(v[j], smask) : v[j]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NREG; ++j) {
+                            uint64_t off = 0;
+#pragma unroll
+                            for (int k = 0; k < RB; ++k)
+                                if ((j >> k) & 1) off += 16ull << P.last_reg_out[k];
+                            __stcs(reinterpret_cast<double2*>(pb + off), make_double2(v[2 * j], v[2 * j + 1]));
+                        }
                     }
                 }
             } else {
@@ -853,24 +897,37 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 // tile boundary: the previous tile's last round (other warps) must be done reading
                 if (r == 0 && (flags & kPassFuseLoad)) __syncthreads();
                 if (split) {
+                    uint32_t bh[1 << HS], lo[1 << HS];
+#pragma unroll
+                    for (int c = 0; c < (1 << HS); ++c) {
+                        uint32_t hi = 0, l = 0;
+#pragma unroll
+                        for (int k = 0; k < HS; ++k) {
+                            if ((c >> k) & 1) hi += rb[HS + k];
+                            if ((c >> k) & 1) l += rb[k];
+                        }
+                        bh[c] = ((__builtin_popcount(c) & 1) ? boff1 : boff) + hi;
+                        lo[c] = l;
+                    }
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
-                        uint32_t off = 0;
-#pragma unroll
-                        for (int k = 0; k < RS; ++k)
-                            if ((j >> k) & 1) off += rb[k];
                         const bool fj = __builtin_popcount(j >> HS) & 1;
-                        sts64((fj ? boff1 : boff) + off, fj ? flip_sign(v[j], smask) : v[j]);
+                        sts64(bh[j >> HS] + lo[j & ((1 << HS) - 1)], fj ? flip_sign(v[j], smask) : v[j]);
                     }
                 } else {
+                    uint32_t bh[8], lo[4];
 #pragma unroll
-                    for (int j = 0; j < NREG; ++j) {
-                        uint32_t off = 0;
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t hi = 0;
 #pragma unroll
-                        for (int k = 0; k < RB; ++k)
-                            if ((j >> k) & 1) off += rb[k];
-                        sts128(boff + off, make_double2(v[2 * j], v[2 * j + 1]));
+                        for (int k = 0; k < 3; ++k)
+                            if ((c >> k) & 1) hi += rb[2 + k];
+                        bh[c] = boff + hi;
                     }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) lo[c] = ((c & 1) ? rb[0] : 0u) + ((c & 2) ? rb[1] : 0u);
+#pragma unroll
+                    for (int j = 0; j < NREG; ++j) sts128(bh[j >> 2] + lo[j & 3], make_double2(v[2 * j], v[2 * j + 1]));
                 }
                 if ((hdr.w >> 16) & 1u) __syncthreads();
                 else __syncwarp();
