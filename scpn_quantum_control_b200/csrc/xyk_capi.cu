@@ -268,6 +268,10 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
         d.st_lsrc[m] = (uint8_t)order[m];
         d.st_odst[m] = (uint8_t)pp.out_of_in[order[m]];
     }
+    {
+        const PlanRound& r0 = pp.rounds.front();
+        for (int k = 0; k < (r0.split ? kRB + 1 : kRB); ++k) d.arr_reg[k] = arrival_stride_bytes(r0.regpos[k]);
+    }
     const PlanRound& last = pp.rounds.back();
     const int last_nreg = last.split ? kRB + 1 : kRB;
     for (int b = 0; b < kTB - last_nreg; ++b) d.last_thr_out[b] = (uint8_t)pp.out_of_in[last.thrpos[b]];

@@ -407,6 +407,7 @@ struct PassDesc {
     uint8_t st_odst[16];     //                that output bit
     uint8_t last_thr_out[8]; // fused store: output bit of the qubit on thread bit b (split: b + 1) of the LAST round
     uint8_t last_reg_out[8]; //              output bit of the qubit on register bit k of the LAST round
+    uint32_t arr_reg[8];     // fused load: byte stride of round 0's register bit k in the arrival layout (arrival_stride_bytes)
     uint64_t out_base;       // peer passes: output-index contribution of this device's rank bits
     double ph_const;         // fused phase: contribution of the sharded (rank) bits, constant on this device
     double ph_tau;           // fused phase: exp(+i tau sum_b w_b (1 - 2 bit_b)) over all input bits
@@ -506,14 +507,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// one thread: the generic-proxy reads of the buffer are ordered before the async-proxy write, the
-// mbarrier expects `bytes`, the copy completes on it
-__device__ __forceinline__ void bulk_load_tile(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t mbar) {
+// Arrival layout of a bulk-loaded tile: the 2^TB amplitudes arrive as 2^(TB-9) segments of 8 KiB, segment s at
+// byte offset s * (8 KiB + 16): slot0(x) = x + (x >> 9).  Additive like pad_slot, and the 16-byte-column
+// strides of positions 0, 1, 2 AND of positions 9, 10, 11 are 1, 2, 4 (mod 8): round 0 reads the tile
+// bank-conflict free when its three low lane bits sit on one position of each pair {0, 9}, {1, 10}, {2, 11}
+// -- the schedule compiler parks three of the round's thread qubits on positions 9..11, so the first round
+// is free to hold ANY tile qubits in registers (a plain linear tile would force positions 0..2 onto lanes).
+__host__ __device__ constexpr uint32_t arrival_stride_bytes(int p) { return p < 9 ? (16u << p) : (16u << p) + (16u << (p - 9)); }
+template <int TB>
+constexpr uint32_t arrival_bytes() {
+    return (16u << TB) + (TB > 9 ? ((1u << (TB - 9)) - 1u) * 16u : 0u);
+}
+// one thread: the generic-proxy reads of the buffer are ordered before the async-proxy writes, the
+// mbarrier expects the whole tile, every segment completes on it
+template <int TB>
+__device__ __forceinline__ void bulk_load_tile(uint32_t smem_dst, const double2* gsrc, uint32_t mbar) {
+    constexpr uint32_t kSeg = TB > 9 ? (16u << 9) : (16u << TB);
+    constexpr int kNumSeg = TB > 9 ? (1 << (TB - 9)) : 1;
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst), "l"(gsrc), "r"(bytes),
-                 "r"(mbar)
-                 : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(kSeg * kNumSeg) : "memory");
+#pragma unroll
+    for (int sgm = 0; sgm < kNumSeg; ++sgm)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst + sgm * (kSeg + 16u)),
+                     "l"(reinterpret_cast<const char*>(gsrc) + (size_t)sgm * kSeg), "r"(kSeg), "r"(mbar)
+                     : "memory");
 }
 
 // The per-round descriptors are copied from the kernel parameter (constant bank) into shared memory
@@ -599,16 +616,16 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
         if (bits & 64u) b += g.w;
         return b;
     };
-    // fused global load: unswizzled round-0 index of this thread (complex amplitudes)
+    // fused load: byte offset of this thread's round-0 base amplitude in the arrival layout
     uint32_t lin0 = 0;
     if (first_split) {
 #pragma unroll
         for (int b = 0; b < NT - 1; ++b)
-            if ((tq >> b) & 1u) lin0 |= 1u << P.rounds[0].thrpos[b];
+            if ((tq >> b) & 1u) lin0 += arrival_stride_bytes(P.rounds[0].thrpos[b]);
     } else {
 #pragma unroll
         for (int b = 0; b < NT; ++b)
-            if ((tid >> b) & 1u) lin0 |= 1u << P.rounds[0].thrpos[b];
+            if ((tid >> b) & 1u) lin0 += arrival_stride_bytes(P.rounds[0].thrpos[b]);
     }
     // per-thread constants of the (unfused) load and store phases
     const uint32_t ld_slot = pad_slot(tid);  // index bits [0, NT) <- thread id
@@ -648,12 +665,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     if (tid == 0) mbar_init(mbar_u32, 1);
     __syncthreads();  // tables and mbarrier visible
 
-    // Fused load = the whole 64 KiB tile arrives by ONE bulk asynchronous copy into the (linear) front of the
+    // Fused load = the whole 64 KiB tile arrives by bulk asynchronous copies (eight 8 KiB segments) into the front of the
     // tile buffer; it is issued as soon as the previous tile's last round has read its data out of the
     // buffer, so the global load overlaps that round's arithmetic and the global store.
-    constexpr uint32_t kTileLinearBytes = (uint32_t)(sizeof(double2) << TB);
     uint32_t tile_parity = 0;
-    if ((flags & kPassFuseLoad) && tid == 0) bulk_load_tile(tile_u32, in + ((uint64_t)blockIdx.x << TB), kTileLinearBytes, mbar_u32);
+    if ((flags & kPassFuseLoad) && tid == 0) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)blockIdx.x << TB), mbar_u32);
 
     if (flags & kPassStagger) {
         const uint32_t k = blockIdx.x / ((gridDim.x + 2) / 3);
@@ -696,27 +712,41 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 mbar_wait(mbar_u32, tile_parity);
                 tile_parity ^= 1u;
                 if (split) {
-                    const uint32_t p0 = tile_u32 + (lin0 << 4) + (half << 3);
+                    const uint32_t p0 = tile_u32 + lin0 + (half << 3);
+                    const uint32_t p1 = p0 + 8u - (half << 4);  // elements with f = 1: the other component
+                    uint32_t bh[1 << HS], lo[1 << HS];
+#pragma unroll
+                    for (int c = 0; c < (1 << HS); ++c) {
+                        uint32_t hi = 0, l = 0;
+#pragma unroll
+                        for (int k = 0; k < HS; ++k) {
+                            if ((c >> k) & 1) hi += P.arr_reg[HS + k];
+                            if ((c >> k) & 1) l += P.arr_reg[k];
+                        }
+                        bh[c] = ((__builtin_popcount(c) & 1) ? p1 : p0) + hi;
+                        lo[c] = l;
+                    }
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
-                        uint32_t off = 0;
-#pragma unroll
-                        for (int k = 0; k < RS; ++k)
-                            if ((j >> k) & 1) off += 16u << P.rounds[0].regpos[k];
-                        // component: Re if f(j) == half, f = parity of the right-group bits
-                        const int fj = __builtin_popcount(j >> HS) & 1;
-                        v[j] = lds64((fj ? p0 + 8u - (half << 4) : p0) + off);
-                        if (fj) v[j] = flip_sign(v[j], smask);
+                        v[j] = lds64(bh[j >> HS] + lo[j & ((1 << HS) - 1)]);
+                        if (__builtin_popcount(j >> HS) & 1) v[j] = flip_sign(v[j], smask);
                     }
                 } else {
-                    const uint32_t p0 = tile_u32 + (lin0 << 4);
+                    const uint32_t p0 = tile_u32 + lin0;
+                    uint32_t bh[8], lo[4];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint32_t hi = 0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if ((c >> k) & 1) hi += P.arr_reg[2 + k];
+                        bh[c] = p0 + hi;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) lo[c] = ((c & 1) ? P.arr_reg[0] : 0u) + ((c & 2) ? P.arr_reg[1] : 0u);
 #pragma unroll
                     for (int j = 0; j < NREG; ++j) {
-                        uint32_t off = 0;
-#pragma unroll
-                        for (int k = 0; k < RB; ++k)
-                            if ((j >> k) & 1) off += 16u << P.rounds[0].regpos[k];
-                        const double2 a = lds128(p0 + off);
+                        const double2 a = lds128(bh[j >> 2] + lo[j & 3]);
                         v[2 * j] = a.x;
                         v[2 * j + 1] = a.y;
                     }
@@ -777,7 +807,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             // the last round holds the tile in registers: the buffer is free for the next tile
             if ((flags & kPassFuseLoad) && (flags & kPassFuseStore) && r == nr - 1) {
                 __syncthreads();
-                if (tid == 0 && t + gridDim.x < ntiles) bulk_load_tile(tile_u32, in + ((t + gridDim.x) << TB), kTileLinearBytes, mbar_u32);
+                if (tid == 0 && t + gridDim.x < ntiles) bulk_load_tile<TB>(tile_u32, in + ((t + gridDim.x) << TB), mbar_u32);
             }
 
             // ---------------- diagonal phase (complex round 0 only) ----------------
@@ -953,7 +983,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             }
             if (flags & kPassFuseLoad) {
                 __syncthreads();
-                if (tid == 0 && t + gridDim.x < ntiles) bulk_load_tile(tile_u32, in + ((t + gridDim.x) << TB), kTileLinearBytes, mbar_u32);
+                if (tid == 0 && t + gridDim.x < ntiles) bulk_load_tile<TB>(tile_u32, in + ((t + gridDim.x) << TB), mbar_u32);
             }
         }
     }

@@ -506,17 +506,16 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         const uint64_t shared_next = rp.tmask & next_tile(p);
         const int s = popc(shared_next);
         RawRound best;
-        if (cfg.fuse_io && s - c_lane >= 0) {
-            const int budget = (s - c_lane + 1) / 2;
-            search_round(rp, g, cdone[p], true, shared_next, budget, 0, best);
-        }
+        // fused store: the c_lane lowest output bits must carry shared qubits that this round keeps on lanes;
+        // every other shared qubit may sit in registers (the next pass's bulk tile load does not care)
+        if (cfg.fuse_io && s - c_lane >= 0) search_round(rp, g, cdone[p], true, shared_next, s - c_lane, 0, best);
         if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
         if (best.cidx.empty()) throw std::runtime_error("compile_plan: last-round search made no progress");
         if (best.split && best.cidx.size() == rp.gate_idx.size() && rp.has_phase) {
             // a single round that also carries the diagonal phase must hold whole complex amplitudes
             allow_split = false;
             best = RawRound();
-            if (cfg.fuse_io && s - c_lane >= 0) search_round(rp, g, cdone[p], true, shared_next, (s - c_lane + 1) / 2, 0, best);
+            if (cfg.fuse_io && s - c_lane >= 0) search_round(rp, g, cdone[p], true, shared_next, s - c_lane, 0, best);
             if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
             allow_split = can_split;
         }
@@ -538,11 +537,13 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         const bool hinted = pm < 0 && !cfg.cyclic && cfg.prev_tile_hint;
         const uint64_t shared_prev = pm < 0 ? (hinted ? (rp.tmask & cfg.prev_tile_hint) : 0) : (rp.tmask & raw[pm].tmask);
         const uint64_t rl_prev = pm < 0 ? (hinted ? cfg.prev_rlast_hint : 0) : rlast[pm];
-        const int budget = popc(shared_prev) - c_lane - popc(rl_prev & shared_prev);
+        // the first round is unconstrained: its tile arrives by bulk copies in the segmented arrival layout
+        // (xyk_kernels.cuh, arrival_stride_bytes) whose conflict-free lane positions the layout step provides
+        (void)shared_prev;
+        (void)rl_prev;
         RawRound best;
         allow_split = can_split && !rp.has_phase;  // the fused phase multiplies whole complex amplitudes
-        if (cfg.fuse_io && (pm >= 0 || hinted) && budget >= 0) search_round(rp, g, cdone[p], false, shared_prev, budget, rl_prev, best);
-        if (best.cidx.empty()) search_round(rp, g, cdone[p], false, 0, 99, rl_prev, best);
+        search_round(rp, g, cdone[p], false, 0, 99, 0, best);
         allow_split = can_split;
         if (best.cidx.empty()) throw std::runtime_error("compile_plan: first-round search made no progress");
         for (int c : best.cidx) cdone[p][c] = 1;
@@ -573,13 +574,16 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         const uint64_t rl_prev = pm < 0 ? (hinted ? cfg.prev_rlast_hint : 0) : rlast[pm];
         perm.assign(nq, -1);
         int pos = 0;
+        // lowest: shared qubits the previous last round keeps on lanes (coalesced fused store; those that
+        // this first round also keeps on lanes first), then the other shared qubits, then the rest of the
+        // tile with the first round's THREAD qubits last: they land on the top tile positions, the second
+        // set of conflict-free lane positions of the arrival layout
         const uint64_t shared = tile & prev;
-        const uint64_t avoid = rl_prev | rfirst[p];
         nshared = popc(shared);
-        nfree = popc(shared & ~avoid);
+        nfree = popc(shared & ~rl_prev);
         const uint64_t rest = tile & ~shared;
-        const uint64_t classes[6] = {shared & ~avoid, shared & rl_prev & ~rfirst[p], shared & rfirst[p] & ~rl_prev,
-                                     shared & rfirst[p] & rl_prev, rest & ~rfirst[p], rest & rfirst[p]};
+        const uint64_t classes[6] = {shared & ~rl_prev & ~rfirst[p], shared & ~rl_prev & rfirst[p], shared & rl_prev & rfirst[p],
+                                     shared & rl_prev & ~rfirst[p], rest & rfirst[p], rest & ~rfirst[p]};
         for (uint64_t cls : classes)
             for (int q = 0; q < nq; ++q)
                 if ((cls >> q) & 1) perm[q] = pos++;
@@ -676,7 +680,13 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         // fused global I/O is possible when the lowest c_lane physical bits (before / after the
         // pass) carry qubits that the first / last round does not hold in registers
         bool fl = cfg.fuse_io && nq > TB, fs = cfg.fuse_io && nq > TB;
-        for (int b = 0; b < c_lane && fl; ++b) fl = !((rfirst[p] >> inv[b]) & 1);
+        // bulk tile load: one thread (non-register) qubit of round 0 on each conflict-free position pair {b, 9 + b}
+        int load_lane[3] = {-1, -1, -1};
+        for (int b = 0; b < c_lane && b < 3 && fl; ++b) {
+            if (!((rfirst[p] >> inv[b]) & 1)) load_lane[b] = b;
+            else if (9 + b < TB && !((rfirst[p] >> inv[9 + b]) & 1)) load_lane[b] = 9 + b;
+            else fl = false;
+        }
         {
             std::vector<int> inv_next(kMaxQ + 8, -1);
             for (int q = 0; q < nq; ++q) inv_next[layouts[p + 1][q]] = q;
@@ -699,7 +709,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         std::vector<uint64_t> forced(nrounds, 0);  // qubits that must be LANE bits in that round
         {
             if (fl)
-                for (int b = 0; b < c_lane; ++b) forced[0] |= 1ull << inv[b];
+                for (int b = 0; b < c_lane && b < 3; ++b) forced[0] |= 1ull << inv[load_lane[b]];
             if (fs) {
                 // lanes of the last round follow ascending output position: the 5 lowest
                 std::vector<int> cand;
@@ -766,7 +776,10 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             const int nl = (int)lanepos.size();
             std::vector<int> order;
             if (r == 0 && fl) {
-                order = lanepos;  // ascending: lanes 0.. sit on the lowest physical bits
+                // the three conflict-free positions of the arrival layout first, the other lanes ascending
+                for (int b = 0; b < c_lane && b < 3; ++b) order.push_back(load_lane[b]);
+                for (int lp : lanepos)
+                    if (std::find(order.begin(), order.end(), lp) == order.end()) order.push_back(lp);
             } else if (r == nrounds - 1 && fs) {
                 order = lanepos;  // ascending OUTPUT position: lanes 0.. write contiguous addresses
                 std::sort(order.begin(), order.end(), [&](int a, int b) { return pp.out_of_in[a] < pp.out_of_in[b]; });

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <cstring>
 
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
     double2 v;
@@ -368,6 +369,269 @@ __global__ void __launch_bounds__(128, 3) pass_split_cpasync(const double* __res
     }
 }
 
+// Realism ladder for split rounds with the TMA tile load: start from pass_split_tma and add the real kernel's
+// features one by one.
+//  F & 1 : sign fix-ups (odd half keeps the f = 1 elements negated: LOP3 on 32 of 64 values at load and store)
+//  F & 2 : runtime gate mask (nine slot branches), coefficients from the constant bank
+//  F & 4 : runtime strides: per-round header from shared memory, 8 high bases + 8 uniform low offsets
+//  F & 8 : per-thread base from seven thread-bit strides (second header word)
+//  F & 16: global store with runtime 64-bit offsets (output bit positions from the descriptor)
+//  F & 32: per-tile output base from a loop over the tile-id bits
+struct SplitDesc {
+    uint16_t rs[16][8];      // register-bit byte strides per round
+    uint16_t ts[16][8];      // thread-bit byte strides per round
+    uint32_t mask[16];
+    double ca[16][10], cb[16][10];
+    uint8_t last_reg_out[8], last_thr_out[8], hi_out[40];
+    int nq;
+};
+__device__ __forceinline__ double flip_sign(double v, uint32_t signmask) {
+    return __hiloint2double(__double2hiint(v) ^ (int)signmask, __double2loint(v));
+}
+template <int F>
+__global__ void __launch_bounds__(128, 3) pass_split_real(const double* __restrict__ in, double* __restrict__ out, int nb, int c, int R,
+                                                          const __grid_constant__ SplitDesc D, double ca0, double cb0) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long mbar_storage;
+    __shared__ __align__(16) uint4 hdr_tab[32];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&mbar_storage);
+    const uint32_t hdr_u32 = (uint32_t)__cvta_generic_to_shared(hdr_tab);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t half = tid & 1u, tq = tid >> 1, smask = half << 31;
+    const uint64_t ntiles = 1ull << (nb - 12);
+    const int abits = 12 - c;
+    if (tid < 16) {
+        hdr_tab[2 * tid] = make_uint4(D.rs[tid][0] | D.rs[tid][1] << 16, D.rs[tid][2] | D.rs[tid][3] << 16, D.rs[tid][4] | D.rs[tid][5] << 16,
+                                      D.mask[tid] | 1u << 16 | 1u << 17);
+        hdr_tab[2 * tid + 1] = make_uint4(D.ts[tid][0] | D.ts[tid][1] << 16, D.ts[tid][2] | D.ts[tid][3] << 16, D.ts[tid][4] | D.ts[tid][5] << 16,
+                                          D.ts[tid][6]);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint64_t t) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(65536u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(base),
+                     "l"(in + (t << 13)), "r"(65536u), "r"(mbar)
+                     : "memory");
+    };
+    auto thread_base = [&](const uint4& g) -> uint32_t {
+        uint32_t b = half << 3;
+        if (tq & 1u) b += g.x & 0xffffu;
+        if (tq & 2u) b += g.x >> 16;
+        if (tq & 4u) b += g.y & 0xffffu;
+        if (tq & 8u) b += g.y >> 16;
+        if (tq & 16u) b += g.z & 0xffffu;
+        if (tq & 32u) b += g.z >> 16;
+        return b;
+    };
+    // fixed-pattern base: warp-private 16 KiB window, 8-byte units (as pass_split)
+    const uint32_t w0 = base + warp * 16384u + lane * 8u;
+    if (tid == 0 && blockIdx.x < ntiles) issue(blockIdx.x);
+    uint32_t phase = 0;
+    uint64_t st_d = 0;
+    if (F & 16) {
+#pragma unroll
+        for (int b = 0; b < 6; ++b)
+            if ((tq >> b) & 1u) st_d |= 1ull << D.last_thr_out[b];
+    }
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        uint64_t obase;
+        if (F & 32) {
+            obase = 0;
+            for (int b = 0; b < D.nq - 12; ++b)
+                if ((t >> b) & 1ull) obase |= 1ull << D.hi_out[b];
+        } else {
+            const uint64_t a_ = t & ((1ull << abits) - 1), rest = t >> abits;
+            obase = (a_ << c) | (rest << (24 - c));
+        }
+        double a[64];
+        uint4 hdr = make_uint4(0, 0, 0, 0), thr = hdr;
+        if (F & 4) {
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hdr.x), "=r"(hdr.y), "=r"(hdr.z), "=r"(hdr.w) : "r"(hdr_u32));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(thr.x), "=r"(thr.y), "=r"(thr.z), "=r"(thr.w) : "r"(hdr_u32 + 16));
+        }
+        uint32_t boff = (F & 8) ? base + thread_base(thr) : w0;
+        mbar_wait(mbar, phase);
+        phase ^= 1;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            a[k] = lds64(base + (k * 128 + tid) * 8u);
+            if ((F & 1) && (__builtin_popcount(k >> 3) & 1)) a[k] = flip_sign(a[k], smask);
+        }
+        for (int r = 0; r < R; ++r) {
+            uint32_t rb[6];
+            uint32_t mask = 0x1ff;
+            if (F & 4) {
+                rb[0] = hdr.x & 0xffffu; rb[1] = hdr.x >> 16; rb[2] = hdr.y & 0xffffu; rb[3] = hdr.y >> 16; rb[4] = hdr.z & 0xffffu; rb[5] = hdr.z >> 16;
+                mask = hdr.w & 0xffffu;
+            }
+            const uint32_t boff1 = boff + 8u - (half << 4);
+            if (r > 0) {
+                if (F & 4) {
+                    uint32_t bh[8], lo[8];
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        uint32_t hi = 0, l = 0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            if ((cc >> k) & 1) hi += rb[3 + k];
+                            if ((cc >> k) & 1) l += rb[k];
+                        }
+                        bh[cc] = ((__builtin_popcount(cc) & 1) ? boff1 : boff) + hi;
+                        lo[cc] = l;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        a[j] = lds64(bh[j >> 3] + lo[j & 7]);
+                        if ((F & 1) && (__builtin_popcount(j >> 3) & 1)) a[j] = flip_sign(a[j], smask);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        a[j] = lds64(w0 + ((j * 256) ^ ((r & 1) << 9)));
+                        if ((F & 1) && (__builtin_popcount(j >> 3) & 1)) a[j] = flip_sign(a[j], smask);
+                    }
+                }
+            }
+            if (r + 1 == R && R > 1) {
+                __syncthreads();
+                if (tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
+            }
+#pragma unroll
+            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                for (int y = 3; y < 6; ++y) {
+                    const int slot = 3 * x + (y - 3);
+                    if (!(F & 2) || (mask & (1u << slot))) {
+                        const double ca = (F & 2) ? D.ca[r][slot] : ca0, cb = (F & 2) ? D.cb[r][slot] : cb0;
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) {
+                            const int lowm = m & ((1 << x) - 1);
+                            const int midm = (m >> x) & ((1 << (y - x - 1)) - 1);
+                            const int him = m >> (y - 1);
+                            const int j0 = lowm | (midm << (x + 1)) | (him << (y + 1));
+                            const int jA = j0 | (1 << x), jB = j0 | (1 << y);
+                            if (__builtin_popcount(jA >> 3) & 1) {
+                                double& X = a[jB]; double& Y = a[jA];
+                                X = fma(ca, Y, X); Y = fma(cb, X, Y); X = fma(ca, Y, X);
+                            } else {
+                                double& X = a[jA]; double& Y = a[jB];
+                                X = fma(ca, Y, X); Y = fma(cb, X, Y); X = fma(ca, Y, X);
+                            }
+                        }
+                    }
+                }
+            if (r + 1 < R) {
+                uint4 hn = hdr, tn = thr;
+                if (F & 4) {
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hn.x), "=r"(hn.y), "=r"(hn.z), "=r"(hn.w) : "r"(hdr_u32 + (r + 1) * 32));
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(tn.x), "=r"(tn.y), "=r"(tn.z), "=r"(tn.w) : "r"(hdr_u32 + (r + 1) * 32 + 16));
+                }
+                if (r == 0) __syncthreads();
+                if (F & 4) {
+                    uint32_t bh[8], lo[8];
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        uint32_t hi = 0, l = 0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            if ((cc >> k) & 1) hi += rb[3 + k];
+                            if ((cc >> k) & 1) l += rb[k];
+                        }
+                        bh[cc] = ((__builtin_popcount(cc) & 1) ? boff1 : boff) + hi;
+                        lo[cc] = l;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        const bool fj = __builtin_popcount(j >> 3) & 1;
+                        sts64(bh[j >> 3] + lo[j & 7], ((F & 1) && fj) ? flip_sign(a[j], smask) : a[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) {
+                        const bool fj = __builtin_popcount(j >> 3) & 1;
+                        sts64(w0 + j * 256, ((F & 1) && fj) ? flip_sign(a[j], smask) : a[j]);
+                    }
+                }
+                __syncthreads();
+                hdr = hn;
+                thr = tn;
+                if (F & 8) boff = base + thread_base(tn);
+            }
+        }
+        if (R == 1) {
+            __syncthreads();
+            if (tid == 0 && t + gridDim.x < ntiles) issue(t + gridDim.x);
+        }
+        if (F & 16) {
+            char* pb = reinterpret_cast<char*>(out) + ((obase + st_d) << 4);
+            char* pb0 = pb + (half << 3);
+            char* pb1 = pb + 8 - (half << 3);
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                uint64_t off = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    if ((j >> k) & 1) off += 16ull << D.last_reg_out[k];
+                const bool fj = __builtin_popcount(j >> 3) & 1;
+                __stcs(reinterpret_cast<double*>((fj ? pb1 : pb0) + off), ((F & 1) && fj) ? flip_sign(a[j], smask) : a[j]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 64; ++k) {
+                const uint32_t o = (k * 128 + tid) >> 1;
+                const uint64_t dst = obase | (o & ((1u << c) - 1)) | ((uint64_t)(o >> c) << 12);
+                const bool fj = __builtin_popcount(k >> 3) & 1;
+                __stcs(out + 2 * dst + (tid & 1), ((F & 1) && fj) ? flip_sign(a[k], smask) : a[k]);
+            }
+        }
+    }
+}
+
+template <int F>
+void run_split_real(const double* a, double* b, int nb, cudaEvent_t e0, cudaEvent_t e1) {
+    cudaFuncSetAttribute(pass_split_real<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75008);
+    SplitDesc D;
+    memset(&D, 0, sizeof(D));
+    D.nq = nb;
+    auto pad = [](uint32_t x) { return x + (x >> 3) + (x >> 6) + (x >> 9); };
+    for (int r = 0; r < 16; ++r) {
+        // registers on tile positions 6..11, thread qubits on positions 0..5 (lanes 1..3 on positions 0,1,2: conflict free)
+        for (int k = 0; k < 6; ++k) D.rs[r][k] = (uint16_t)(16 * pad(1u << (6 + k)));
+        for (int k = 0; k < 6; ++k) D.ts[r][k] = (uint16_t)(16 * pad(1u << k));
+        D.mask[r] = 0x1ff;
+        for (int k = 0; k < 10; ++k) { D.ca[r][k] = 1e-9; D.cb[r][k] = -1e-9; }
+    }
+    // output permutation: thread qubits (positions 0..5) -> output bits 0..5; registers (6..11) -> bits 12..17; tile id bits fill the rest
+    for (int k = 0; k < 6; ++k) { D.last_thr_out[k] = (uint8_t)k; D.last_reg_out[k] = (uint8_t)(12 + k); }
+    {
+        int nxt = 6;
+        for (int b = 0; b < nb - 12; ++b) {
+            while (nxt >= 12 && nxt < 18) ++nxt;
+            D.hi_out[b] = (uint8_t)nxt++;
+            if (nxt == 12) nxt = 18;
+        }
+    }
+    for (int R : {2, 4, 5}) {
+        float best = 1e30f;
+        for (int it = 0; it < 3; ++it) {
+            cudaEventRecord(e0);
+            pass_split_real<F><<<148 * 3, 128, 75008>>>(a, b, nb, 5, R, D, 1e-9, -1e-9);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (it > 0 && ms < best) best = ms;
+        }
+        printf("split-real F=%2d R=%d : %.3f ms per pass\n", F, R, best);
+    }
+}
+
 // Realism ladder for the complex round: which feature of the real kernel costs what?
 //  F & 1: runtime XOR addressing (per-thread base ^ xor-combination of five runtime register-bit offsets)
 //  F & 2: runtime gate mask (ten slot branches) with coefficients fetched from shared memory one gate ahead
@@ -631,6 +895,14 @@ int main() {
         printf("split+TMA load: R=%d rounds x 9 gates = %2d gates : %.3f ms per pass  %.0f GB/s (%.1f%%)\n", R, 9 * R, best, gb / (best * 1e-3),
                100.0 * gb / (best * 1e-3) / 6541.5);
     }
+    run_split_real<0>((const double*)a, (double*)b, nb, e0, e1);
+    run_split_real<1>((const double*)a, (double*)b, nb, e0, e1);
+    run_split_real<2>((const double*)a, (double*)b, nb, e0, e1);
+    run_split_real<12>((const double*)a, (double*)b, nb, e0, e1);
+    run_split_real<14>((const double*)a, (double*)b, nb, e0, e1);
+    run_split_real<16>((const double*)a, (double*)b, nb, e0, e1);
+    run_split_real<48>((const double*)a, (double*)b, nb, e0, e1);
+    run_split_real<63>((const double*)a, (double*)b, nb, e0, e1);
     cudaFuncSetAttribute(pass_split_tma<9, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75008);
     cudaFuncSetAttribute(pass_split_tma<9, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75008);
     for (int rows : {512, 128})
