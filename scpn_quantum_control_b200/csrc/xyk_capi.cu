@@ -340,6 +340,7 @@ void apply_env(SchedConfig& cfg) {
     if (const char* e = std::getenv("XYK_LANE_BITS")) cfg.lane_bits = std::atoi(e);
     if (const char* e = std::getenv("XYK_NEED_SHARED")) cfg.need_shared = std::atoi(e);
     if (const char* e = std::getenv("XYK_SPLIT")) cfg.split_rounds = std::atoi(e) != 0;
+    if (const char* e = std::getenv("XYK_SPLIT_ANY")) cfg.split_any = std::atoi(e) != 0;
     if (const char* e = std::getenv("XYK_SPLIT_MARGIN")) cfg.split_margin = std::atoi(e);
 }
 
@@ -443,7 +444,11 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
             if (ablate & 32) d.flags |= kPassPfLate;
             if (ablate & 64) d.flags |= kPassPfEvictLast;
             if (ablate & 128) d.flags |= kPassPlainLd;
-            if (ablate & 256) d.flags |= kPassStagger;
+            if (ablate & 256) {
+                d.flags |= kPassStagger;
+                static const int stns = std::getenv("XYK_STAGGER_NS") ? std::atoi(std::getenv("XYK_STAGGER_NS")) : 4000;
+                d.pad0 = stns;
+            }
             if (ablate & 8) for (int r = 0; r < d.nrounds; ++r) d.rounds[r].cta_sync = 0;
             tile_pass_kernel<kTB, kRB, true, 3, false><<<grid, nthr, smem, h->stream>>>(in, out, d, ntiles, peers);
         } else if (peer) {

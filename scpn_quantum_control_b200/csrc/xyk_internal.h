@@ -62,6 +62,7 @@ struct PlanRound {
     int cta_sync_after;  // 1: block-wide barrier after this round's exchange, 0: the data stays inside each warp
     int split;        // 1: split round
     int nreg;         // register qubits of this round (RB, or RB + 1 for split rounds)
+    int nleft;        // split rounds: size of the left group (nreg / 2 unless SchedConfig::split_any)
 };
 
 struct PlanPass {
@@ -97,6 +98,7 @@ struct SchedConfig {
     int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
     bool split_rounds = true;  // allow split rounds (RB + 1 register qubits over two real half-states)
+    bool split_any = false;    // split rounds may use unbalanced bipartitions (1 | RB, 2 | RB - 1) of the register qubits
     int split_margin = 1;      // a split round must run at least this many more gates than the best complex round
                                // (it moves the same bytes with twice as many shared-memory instructions)
     bool cyclic = true;    // the program ends in its own start layout (it can be replayed back to back)

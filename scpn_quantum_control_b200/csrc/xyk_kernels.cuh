@@ -672,8 +672,16 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     if ((flags & kPassFuseLoad) && tid == 0) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)blockIdx.x << TB), mbar_u32);
 
     if (flags & kPassStagger) {
+        // co-resident CTAs (block ids i, i + #SM, i + 2 #SM) start pad0 ns apart (spin on the ns timer)
         const uint32_t k = blockIdx.x / ((gridDim.x + 2) / 3);
-        for (uint32_t i = 0; i < k * 5; ++i) __nanosleep(1000);
+        if (k) {
+            uint64_t t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (t1 - t0 < (uint64_t)k * (uint64_t)P.pad0);
+        }
     }
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const double2* src = in + (t << TB);

@@ -409,32 +409,38 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         best.cidx.clear();
         best.split = true;
         if (tn < RS) return;
-        const int H = RS / 2;
-        std::vector<int> idx(RS), sub(H), ex;
+        // left-group sizes: RS/2 | RS/2 always; with cfg.split_any also the unbalanced bipartitions (1 | RS-1, 2 | RS-2, ...)
+        const int Hmin = cfg.split_any ? 1 : RS / 2;
+        std::vector<int> idx(RS), ex;
         for (int k = 0; k < RS; ++k) idx[k] = k;
         int best_pref = -1;
         while (true) {
             uint64_t sm = 0;
             for (int k = 0; k < RS; ++k) sm |= 1ull << tq[idx[k]];
             if (popc(sm & limit_mask) <= limit) {
-                // left groups containing the smallest element (the mirrored split runs the same gates)
-                for (int k = 0; k < H; ++k) sub[k] = k;
-                while (true) {
-                    uint64_t lm = 0;
-                    for (int k = 0; k < H; ++k) lm |= 1ull << tq[idx[sub[k]]];
-                    split_closure(g, rp.gate_idx, cdone, lm, sm & ~lm, reverse_scan, ex);
-                    const int pref = popc(sm & prefer);
-                    if (ex.size() > best.cidx.size() || (ex.size() == best.cidx.size() && !ex.empty() && pref > best_pref)) {
-                        best.cidx = ex;
-                        best.rmask = sm;
-                        best.lmask = lm;
-                        best_pref = pref;
+                for (int H = RS / 2; H >= Hmin; --H) {
+                    std::vector<int> sub(H);
+                    for (int k = 0; k < H; ++k) sub[k] = k;
+                    while (true) {
+                        // balanced split: left groups containing the smallest element only (the mirrored split runs the same gates)
+                        if (!(2 * H == RS && sub[0] != 0)) {
+                            uint64_t lm = 0;
+                            for (int k = 0; k < H; ++k) lm |= 1ull << tq[idx[sub[k]]];
+                            split_closure(g, rp.gate_idx, cdone, lm, sm & ~lm, reverse_scan, ex);
+                            const int pref = popc(sm & prefer);
+                            if (ex.size() > best.cidx.size() || (ex.size() == best.cidx.size() && !ex.empty() && pref > best_pref)) {
+                                best.cidx = ex;
+                                best.rmask = sm;
+                                best.lmask = lm;
+                                best_pref = pref;
+                            }
+                        }
+                        int k = H - 1;
+                        while (k >= 0 && sub[k] == RS - H + k) --k;
+                        if (k < 0) break;
+                        ++sub[k];
+                        for (int m = k + 1; m < H; ++m) sub[m] = sub[m - 1] + 1;
                     }
-                    int k = H - 1;
-                    while (k >= 1 && sub[k] == RS - H + k) --k;
-                    if (k < 1) break;  // sub[0] stays 0
-                    ++sub[k];
-                    for (int m = k + 1; m < H; ++m) sub[m] = sub[m - 1] + 1;
                 }
             }
             int k = RS - 1;
@@ -755,6 +761,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 }
                 rq = lq;
                 rq.insert(rq.end(), rgt.begin(), rgt.end());
+                pr.nleft = (int)lq.size();
             } else {
                 for (int q = 0; q < nq; ++q)
                     if ((R.rmask >> q) & 1) rq.push_back(q);
@@ -822,8 +829,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 }
                 int slot = 0;
                 if (R.split) {
-                    if (a < 0 || b < RS / 2 || a >= RS / 2) throw std::runtime_error("compile_plan: split round gate inside one group");
-                    slot = (RS / 2) * a + (b - RS / 2);
+                    if (a < 0 || b < pr.nleft || a >= pr.nleft) throw std::runtime_error("compile_plan: split round gate inside one group");
+                    slot = (RS - pr.nleft) * a + (b - pr.nleft);
                 } else {
                     for (int x = 0; x < a; ++x) slot += RB - 1 - x;
                     slot += b - a - 1;
@@ -1111,7 +1118,7 @@ std::string plan_to_json(const Plan& plan) {
         for (size_t r = 0; r < pp.rounds.size(); ++r) {
             const PlanRound& pr = pp.rounds[r];
             const int nreg = pr.nreg ? pr.nreg : plan.RB;
-            os << (r ? "," : "") << "{\"split\":" << pr.split << ",\"regq\":[";
+            os << (r ? "," : "") << "{\"split\":" << pr.split << ",\"nleft\":" << pr.nleft << ",\"regq\":[";
             for (int k = 0; k < nreg; ++k) os << (k ? "," : "") << pr.regq[k];
             os << "],\"regpos\":[";
             for (int k = 0; k < nreg; ++k) os << (k ? "," : "") << pr.regpos[k];
@@ -1120,11 +1127,11 @@ std::string plan_to_json(const Plan& plan) {
             os << "],\"mask\":" << pr.mask << ",\"cta_sync_after\":" << pr.cta_sync_after << ",\"gates\":[";
             bool firstg = true;
             if (pr.split) {
-                const int H = nreg / 2;
-                for (int a = 0; a < H; ++a)
-                    for (int b = 0; b < H; ++b)
-                        if ((pr.mask >> (H * a + b)) & 1) {
-                            os << (firstg ? "" : ",") << "[" << pr.regq[a] << "," << pr.regq[H + b] << "," << pr.phi[H * a + b] << "]";
+                const int HL = pr.nleft, HR = nreg - pr.nleft;
+                for (int a = 0; a < HL; ++a)
+                    for (int b = 0; b < HR; ++b)
+                        if ((pr.mask >> (HR * a + b)) & 1) {
+                            os << (firstg ? "" : ",") << "[" << pr.regq[a] << "," << pr.regq[HL + b] << "," << pr.phi[HR * a + b] << "]";
                             firstg = false;
                         }
             } else {
