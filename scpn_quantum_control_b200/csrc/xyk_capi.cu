@@ -313,7 +313,7 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
         const PlanRound& pr = rounds_used[r];
         Desc::Round& R = d.rounds[r];
         const int nreg = pr.split ? kRB + 1 : kRB;
-        R.split = (uint16_t)(pr.split ? 1 : 0);
+        R.split = (uint16_t)(pr.split ? pr.nleft : 0);  // 0: complex round, else the left-group size of the split round
         for (int b = 0; b < kTB - nreg; ++b) R.thrpos[b] = (uint8_t)pr.thrpos[b];
         for (int k = 0; k < nreg; ++k) {
             R.regpos[k] = (uint8_t)pr.regpos[k];
@@ -340,7 +340,11 @@ void apply_env(SchedConfig& cfg) {
     if (const char* e = std::getenv("XYK_LANE_BITS")) cfg.lane_bits = std::atoi(e);
     if (const char* e = std::getenv("XYK_NEED_SHARED")) cfg.need_shared = std::atoi(e);
     if (const char* e = std::getenv("XYK_SPLIT")) cfg.split_rounds = std::atoi(e) != 0;
-    if (const char* e = std::getenv("XYK_SPLIT_ANY")) cfg.split_any = std::atoi(e) != 0;
+    if (const char* e = std::getenv("XYK_BEAM")) cfg.beam_width = cfg.beam_cands = std::atoi(e);
+    if (const char* e = std::getenv("XYK_FUSE_IO")) cfg.fuse_io = std::atoi(e) != 0;
+    if (const char* e = std::getenv("XYK_UNB_FIRST")) cfg.unb_first = std::atoi(e) != 0;
+    if (const char* e = std::getenv("XYK_UNB_LAST")) cfg.unb_last = std::atoi(e) != 0;
+    if (const char* e = std::getenv("XYK_SPLIT_MIN_LEFT")) cfg.split_min_left = std::atoi(e);
     if (const char* e = std::getenv("XYK_SPLIT_MARGIN")) cfg.split_margin = std::atoi(e);
 }
 
@@ -370,6 +374,7 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
     cfg.RB = kRB;
     cfg.max_rounds = kMaxRounds;
     apply_env(cfg);
+    cfg.split_min_left = std::max(cfg.split_min_left, 2);  // the pass kernel has no 1 | 5 rounds
     prog->plan = compile_plan(h->nlocal, segs, cfg);
     prog->plan.layers1_equiv = l1;
     prog->loc2log.resize(h->nlocal);
@@ -380,14 +385,30 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
     return prog;
 }
 
+// the eight instantiations of the pass kernel: shear-form rotations or not, peer (fused exchange) stores or not,
+// unbalanced (2 | 4) split rounds compiled in or not (the lean kernel is ~30 % smaller)
+using PassKernel = void (*)(const double2*, double2*, const Desc, uint64_t, const PeerPtrs);
+PassKernel pass_kernel_fn(bool lift, bool peer, bool unb) {
+    if (lift) {
+        if (peer) return unb ? tile_pass_kernel<kTB, kRB, true, 3, true, true> : tile_pass_kernel<kTB, kRB, true, 3, true, false>;
+        return unb ? tile_pass_kernel<kTB, kRB, true, 3, false, true> : tile_pass_kernel<kTB, kRB, true, 3, false, false>;
+    }
+    if (peer) return unb ? tile_pass_kernel<kTB, kRB, false, 3, true, true> : tile_pass_kernel<kTB, kRB, false, 3, true, false>;
+    return unb ? tile_pass_kernel<kTB, kRB, false, 3, false, true> : tile_pass_kernel<kTB, kRB, false, 3, false, false>;
+}
+bool desc_unbalanced(const Desc& d) {
+    static const bool force = std::getenv("XYK_FORCE_UNB") != nullptr;  // experiment: always run the larger kernel
+    if (force) return true;
+    for (int r = 0; r < d.nrounds; ++r)
+        if (d.rounds[r].split == 2) return true;
+    return false;
+}
+
 int configure_pass_kernels(xyk_handle h) {
     const int smem = (int)tile_bytes<kTB>();
-    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, true, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, false, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    XYK_CUDA(h, cudaFuncSetAttribute(tile_pass_kernel<kTB, kRB, false, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int k = 0; k < 8; ++k) XYK_CUDA(h, cudaFuncSetAttribute(pass_kernel_fn(k & 1, k & 2, k & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
-    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tile_pass_kernel<kTB, kRB, true, 3, false>, 1 << (kTB - kRB), smem));
+    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel_fn(true, false, false), 1 << (kTB - kRB), smem));
     if (occ < 1) occ = 1;
     h->pass_grid = occ * h->sm_count;
     return XYK_OK;
@@ -418,7 +439,10 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
     if (peer)
         for (int r = 0; r < h->world; ++r) peers.p[r] = (double2*)h->peer_buf[r][h->cur ^ 1];
     int rc;
+    const char* stop_env = std::getenv("XYK_STOP_AFTER_PASS");  // debugging: run only the first k passes of a program
+    const long stop_after = stop_env ? std::atol(stop_env) : -1;
     for (size_t p = p0; p < p1; ++p) {
+        if (stop_after >= 0 && (long)p >= stop_after) break;
         const PlanPass& pp = plan.passes[p];
         if (pp.has_phase && !(prog.descs[p].flags & kPassHasPhase)) {
             rc = apply_phase(h, pp.ztau);
@@ -450,13 +474,9 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
                 d.pad0 = stns;
             }
             if (ablate & 8) for (int r = 0; r < d.nrounds; ++r) d.rounds[r].cta_sync = 0;
-            tile_pass_kernel<kTB, kRB, true, 3, false><<<grid, nthr, smem, h->stream>>>(in, out, d, ntiles, peers);
-        } else if (peer) {
-            if (prog.lift[p]) tile_pass_kernel<kTB, kRB, true, 3, true><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
-            else tile_pass_kernel<kTB, kRB, false, 3, true><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
+            pass_kernel_fn(true, false, desc_unbalanced(d))<<<grid, nthr, smem, h->stream>>>(in, out, d, ntiles, peers);
         } else {
-            if (prog.lift[p]) tile_pass_kernel<kTB, kRB, true, 3, false><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
-            else tile_pass_kernel<kTB, kRB, false, 3, false><<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
+            pass_kernel_fn(prog.lift[p] != 0, peer, desc_unbalanced(prog.descs[p]))<<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
         }
         if (h->stats.timing_enabled) cudaEventRecord(h->pass_events[2 * p + 1], h->stream);
         h->cur ^= 1;
@@ -473,7 +493,7 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
 
 int end_program(xyk_handle h, Program& prog, size_t timed_passes) {
     const Plan& plan = prog.plan;
-    if (plan.has_trailing_phase) {
+    if (plan.has_trailing_phase && !std::getenv("XYK_STOP_AFTER_PASS")) {
         int rc = apply_phase(h, plan.trailing_ztau);
         if (rc) return rc;
     }
@@ -671,6 +691,7 @@ int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1) {
     cfg.max_rounds = kMaxRounds;
     cfg.peer_exchange = h->peers_ready && h->peer_exchange_opt;
     apply_env(cfg);
+    cfg.split_min_left = std::max(cfg.split_min_left, 2);  // the pass kernel has no 1 | 5 rounds
     std::vector<ShardOp> ops;
     try {
         ops = compile_sharded(h->n, current_globals(h), segs, cfg, nullptr);

@@ -62,7 +62,7 @@ struct PlanRound {
     int cta_sync_after;  // 1: block-wide barrier after this round's exchange, 0: the data stays inside each warp
     int split;        // 1: split round
     int nreg;         // register qubits of this round (RB, or RB + 1 for split rounds)
-    int nleft;        // split rounds: size of the left group (nreg / 2 unless SchedConfig::split_any)
+    int nleft;        // split rounds: size of the left group (nreg / 2, or down to SchedConfig::split_min_left)
 };
 
 struct PlanPass {
@@ -98,7 +98,11 @@ struct SchedConfig {
     int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
     bool split_rounds = true;  // allow split rounds (RB + 1 register qubits over two real half-states)
-    bool split_any = false;    // split rounds may use unbalanced bipartitions (1 | RB, 2 | RB - 1) of the register qubits
+    int beam_width = 3;        // round search: states kept per depth (1 = greedy)
+    int beam_cands = 3;        // round search: candidate rounds expanded per state
+    bool unb_first = true, unb_last = true;  // unbalanced split rounds allowed as the first / last round of a pass
+    int split_min_left = 2;    // smallest left group of a split round: 3 = balanced 3 | 3 only, 2 adds 2 | 4 (1 | 5 is
+                               // understood by the compiler but has no kernel: its code made ptxas spill)
     int split_margin = 1;      // a split round must run at least this many more gates than the best complex round
                                // (it moves the same bytes with twice as many shared-memory instructions)
     bool cyclic = true;    // the program ends in its own start layout (it can be replayed back to back)

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "xyk_internal.h"
 
 namespace xyk {
@@ -394,7 +396,8 @@ struct PassDesc {
         uint16_t regsw[8];   // shared-memory byte stride of register bit k: 16 * pad_slot(1 << regpos[k])
         uint32_t mask;       // enabled pair slots
         uint16_t cta_sync;   // 1: block-wide barrier after this round's exchange; 0: warp-level barrier suffices
-        uint16_t split;      // 1: split round (RB + 1 register qubits, one real component per amplitude; see PlanRound)
+        uint16_t split;      // 0: complex round; 2, 3: split round (RB + 1 register qubits, one real component per amplitude;
+                             // see PlanRound) whose left group has that many qubits (the right group sits on the high register bits)
         double ca[NSLOT];    // shear form: -tan(phi/2); standard form: cos(phi)
         double cb[NSLOT];    // sin(phi)
     };
@@ -562,7 +565,107 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v) {
     asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
 }
 
-template <int TB, int RB, bool LIFT, int MINB, bool PEER>
+// Split rounds, NL = size of the left group (register bits [0, NL)), right group on bits [NL, RS).
+// role(j) = parity of the right-group bits of j: the thread of half h holds component role ^ h of
+// amplitude j, negated when role = 1 and h = 1.  Addresses: eight per-thread bases over the three high
+// register bits (component chosen by the parity of those bits) + eight warp-uniform offsets over the
+// three low bits; elements whose LOW bits carry an odd share of the role (NL < 3 only) are served in a
+// second sweep after flipping the component bit (^ 8) of the eight bases.
+template <int NL, int RS, int NV, bool STORE>
+__device__ __forceinline__ void split_exchange(double (&v)[NV], uint32_t base, uint32_t half, const uint32_t (&st)[RS], uint32_t smask) {
+    static_assert(RS == 6 && NV == 64, "address split: three high + three low register bits");
+    const uint32_t base1 = base + 8u - (half << 4);  // the other real component of the same amplitude slot
+    uint32_t bh[8], lo[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint32_t hi = 0, l = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if ((c >> k) & 1) hi += st[3 + k];
+            if ((c >> k) & 1) l += st[k];
+        }
+        bh[c] = ((__builtin_popcount(c) & 1) ? base1 : base) + hi;
+        lo[c] = l;
+    }
+#pragma unroll
+    for (int sweep = 0; sweep < (NL < 3 ? 2 : 1); ++sweep) {
+        if (sweep == 1) {  // elements whose low bits flip the role: the other component
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t hi = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if ((c >> k) & 1) hi += st[3 + k];
+                bh[c] = ((__builtin_popcount(c) & 1) ? base : base1) + hi;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if ((__builtin_popcount((j & 7) >> NL) & 1) != sweep) continue;
+            const bool fj = __builtin_popcount(j >> NL) & 1;
+            if constexpr (STORE) {
+                sts64(bh[j >> 3] + lo[j & 7], fj ? flip_sign(v[j], smask) : v[j]);
+            } else {
+                v[j] = lds64(bh[j >> 3] + lo[j & 7]);
+                if (fj) v[j] = flip_sign(v[j], smask);
+            }
+        }
+    }
+}
+
+template <int NL, int RS, int NV, bool LIFT, typename Round>
+__device__ __forceinline__ void split_gates(double (&v)[NV], uint32_t mask, const Round& R) {
+#pragma unroll
+    for (int x = 0; x < NL; ++x) {
+#pragma unroll
+        for (int y = NL; y < RS; ++y) {
+            const int slot = (RS - NL) * x + (y - NL);
+            if (mask & (1u << slot)) {
+                const double ca = R.ca[slot], cb = R.cb[slot];
+#pragma unroll
+                for (int m = 0; m < NV / 4; ++m) {
+                    const int j0 = insert_zero(insert_zero(m, x), y);
+                    const int jA = j0 | (1 << x), jB = j0 | (1 << y);
+                    // half 0 holds Re(A), Im(B) when role(jA) = 0 and Im(A), Re(B) otherwise (roles swap)
+                    if (__builtin_popcount(jA >> NL) & 1) rotate2<LIFT>(v[jB], v[jA], ca, cb);
+                    else rotate2<LIFT>(v[jA], v[jB], ca, cb);
+                }
+            }
+        }
+    }
+}
+
+template <int NL, int RS, int NV, bool PEER>
+__device__ __forceinline__ void split_global_store(const double (&v)[NV], double2* __restrict__ out, const PeerPtrs& peers, int nq,
+                                                   uint64_t dbase, const uint8_t* last_reg_out, uint32_t half, uint32_t smask) {
+    if constexpr (PEER) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint64_t off = 0;
+#pragma unroll
+            for (int k = 0; k < RS; ++k)
+                if ((j >> k) & 1) off += 1ull << last_reg_out[k];
+            const uint32_t fj = __builtin_popcount(j >> NL) & 1;
+            store_out_comp<PEER>(out, peers, nq, dbase + off, fj ^ half, fj ? flip_sign(v[j], smask) : v[j]);
+        }
+    } else {
+        // per-thread byte pointer once per tile + warp-uniform byte offsets of the register bits
+        char* pb = reinterpret_cast<char*>(out) + (dbase << 4);
+        char* pb0 = pb + (half << 3);      // elements with role 0: component `half`
+        char* pb1 = pb + 8 - (half << 3);  // elements with role 1: the other component
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint64_t off = 0;
+#pragma unroll
+            for (int k = 0; k < RS; ++k)
+                if ((j >> k) & 1) off += 16ull << last_reg_out[k];
+            const bool fj = __builtin_popcount(j >> NL) & 1;
+            __stcs(reinterpret_cast<double*>((fj ? pb1 : pb0) + off), fj ? flip_sign(v[j], smask) : v[j]);
+        }
+    }
+}
+
+template <int TB, int RB, bool LIFT, int MINB, bool PEER, bool UNB>
 __global__ void __launch_bounds__(1 << (TB - RB), MINB)
 tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                  const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles, const __grid_constant__ PeerPtrs peers) {
@@ -572,7 +675,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     static_assert(HS * HS <= NSLOT, "split-round slots share the coefficient table");
     using Round = typename PassDesc<TB, RB>::Round;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // per round: {rs0|rs1<<16, rs2|rs3<<16, rs4|rs5<<16, mask|sync<<16|split<<17}, {ts0|ts1<<16, ts2|ts3<<16, ts4|ts5<<16, ts6}
+    // per round: {rs0|rs1<<16, rs2|rs3<<16, rs4|rs5<<16, mask|sync<<16|nleft<<17 (nleft = 0: complex round)}, {ts0|ts1<<16, ts2|ts3<<16, ts4|ts5<<16, ts6}
     // rs = byte stride of a register bit, ts = byte stride of a thread bit
     __shared__ __align__(16) uint4 hdr_tab[2 * (kMaxRounds + 1)];
     __shared__ __align__(8) unsigned long long tile_mbar;
@@ -593,7 +696,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
         h.x = (uint32_t)R.regsw[0] | ((uint32_t)R.regsw[1] << 16);
         h.y = (uint32_t)R.regsw[2] | ((uint32_t)R.regsw[3] << 16);
         h.z = (uint32_t)R.regsw[4] | ((uint32_t)R.regsw[5] << 16);
-        h.w = (R.mask & 0xffffu) | ((uint32_t)(R.cta_sync ? 1u : 0u) << 16) | ((uint32_t)(R.split ? 1u : 0u) << 17);
+        h.w = (R.mask & 0xffffu) | ((uint32_t)(R.cta_sync ? 1u : 0u) << 16) | ((uint32_t)(R.split & 3u) << 17);
         uint32_t ts[8];
         for (int b = 0; b < 8; ++b) ts[b] = b < (R.split ? NT - 1 : NT) ? 16u * pad_slot(1u << R.thrpos[b]) : 0u;
         g.x = ts[0] | (ts[1] << 16);
@@ -706,7 +809,9 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             rb[3] = hdr.y >> 16;
             rb[4] = hdr.z & 0xffffu;
             rb[5] = hdr.z >> 16;
-            const bool split = (hdr.w >> 17) & 1u;
+            const uint32_t nl = (hdr.w >> 17) & 3u;  // 0: complex round; else the left-group size of a split round
+            const bool split = nl != 0u;
+            const bool unb = UNB && nl == 2u;  // unbalanced (2 | 4) split round: separate code, UNB kernels only
             const uint32_t boff1 = boff + 8u - (half << 4);  // split rounds: base of the elements with f(j) = 1
             if ((flags & kPassPfLate) && !(flags & kPassFuseLoad) && r == nr - 1) prefetch_next();
             const Round& R = P.rounds[r];  // gate coefficients stay in the constant bank: a uniform operand of DFMA
@@ -719,7 +824,13 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             if (r == 0 && (flags & kPassFuseLoad)) {
                 mbar_wait(mbar_u32, tile_parity);
                 tile_parity ^= 1u;
-                if (split) {
+                if (unb) {
+                    if constexpr (UNB) {
+                        uint32_t st[RS];
+                        for (int k = 0; k < RS; ++k) st[k] = P.arr_reg[k];
+                        split_exchange<2, RS, NV, false>(v, tile_u32 + lin0 + (half << 3), half, st, smask);
+                    }
+                } else if (split) {
                     const uint32_t p0 = tile_u32 + lin0 + (half << 3);
                     const uint32_t p1 = p0 + 8u - (half << 4);  // elements with f = 1: the other component
                     uint32_t bh[1 << HS], lo[1 << HS];
@@ -772,7 +883,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 }
                 // address = per-thread base of the high register bits (8 vector adds per burst) + warp-uniform
                 // offset of the low register bits: LDS [R + UR], no per-access vector arithmetic
-                if (split) {
+                if (unb) {
+                    if constexpr (UNB) {
+                        split_exchange<2, RS, NV, false>(v, boff, half, rb, smask);
+                    }
+                } else if (split) {
                     uint32_t bh[1 << HS], lo[1 << HS];
 #pragma unroll
                     for (int c = 0; c < (1 << HS); ++c) {
@@ -839,7 +954,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 
             // ---------------- gates ----------------
             const uint32_t mask = hdr.w & 0xffffu;
-            if (split) {
+            if (unb) {
+                if constexpr (UNB) {
+                    split_gates<2, RS, NV, LIFT>(v, mask, R);
+                }
+            } else if (split) {
 #pragma unroll
                 for (int x = 0; x < HS; ++x) {
 #pragma unroll
@@ -882,7 +1001,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             if (r == nr - 1 && (flags & kPassFuseStore)) {
                 const uint64_t dbase = obase + st_d;
                 if constexpr (PEER) {
-                    if (split) {
+                    if (unb) {
+                        if constexpr (UNB) {
+                            split_global_store<2, RS, NV, PEER>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
+                        }
+                    } else if (split) {
 #pragma unroll
                         for (int j = 0; j < NV; ++j) {
                             uint64_t off = 0;
@@ -905,7 +1028,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 } else {
                     // per-thread byte pointer once per tile + warp-uniform byte offsets of the register bits
                     char* pb = reinterpret_cast<char*>(out) + (dbase << 4);
-                    if (split) {
+                    if (unb) {
+                        if constexpr (UNB) {
+                            split_global_store<2, RS, NV, PEER>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
+                        }
+                    } else if (split) {
                         char* pb0 = pb + (half << 3);          // elements with f = 0: component `half`
                         char* pb1 = pb + 8 - (half << 3);      // elements with f = 1: the other component
 #pragma unroll
@@ -934,7 +1061,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 const uint4 thr_next = lds_u4(hdr_u32 + (uint32_t)(r + 1) * 32u + 16u);
                 // tile boundary: the previous tile's last round (other warps) must be done reading
                 if (r == 0 && (flags & kPassFuseLoad)) __syncthreads();
-                if (split) {
+                if (unb) {
+                    if constexpr (UNB) {
+                        split_exchange<2, RS, NV, true>(v, boff, half, rb, smask);
+                    }
+                } else if (split) {
                     uint32_t bh[1 << HS], lo[1 << HS];
 #pragma unroll
                     for (int c = 0; c < (1 << HS); ++c) {
@@ -970,7 +1101,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 if ((hdr.w >> 16) & 1u) __syncthreads();
                 else __syncwarp();
                 hdr = hdr_next;
-                boff = tile_u32 + thread_base(thr_next, (hdr_next.w >> 17) & 1u);
+                boff = tile_u32 + thread_base(thr_next, ((hdr_next.w >> 17) & 3u) != 0u);
             }
         }
 

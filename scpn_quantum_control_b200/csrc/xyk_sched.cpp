@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <sstream>
 #include <stdexcept>
 
@@ -409,8 +410,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         best.cidx.clear();
         best.split = true;
         if (tn < RS) return;
-        // left-group sizes: RS/2 | RS/2 always; with cfg.split_any also the unbalanced bipartitions (1 | RS-1, 2 | RS-2, ...)
-        const int Hmin = cfg.split_any ? 1 : RS / 2;
+        // left-group sizes: RS/2 | RS/2 always; down to cfg.split_min_left also the unbalanced bipartitions (2 | RS-2, 1 | RS-1)
+        const int Hmin = cfg.unb_last ? std::max(1, std::min(cfg.split_min_left, RS / 2)) : RS / 2;  // search_split serves the last rounds
         std::vector<int> idx(RS), ex;
         for (int k = 0; k < RS; ++k) idx[k] = k;
         int best_pref = -1;
@@ -501,14 +502,147 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         if ((int)sp.cidx.size() >= (int)best.cidx.size() + cfg.split_margin) best = sp;
     };
 
+    // top-K candidate rounds (distinct gate sets) for a beam search; score = 2 * gates - split (ties go to the complex round)
+    struct Pool {
+        size_t K;
+        std::vector<RawRound> v;
+        static int score(const RawRound& r) { return 2 * (int)r.cidx.size() - (r.split ? 1 : 0); }
+        int floor_score() const { return v.size() < K ? 0 : score(v.back()); }
+        void add(const RawRound& r) {
+            if (r.cidx.empty()) return;
+            const int sc = score(r);
+            if (v.size() >= K && sc <= score(v.back())) return;
+            std::vector<int> key(r.cidx);
+            std::sort(key.begin(), key.end());
+            for (auto& o : v) {
+                std::vector<int> ok(o.cidx);
+                std::sort(ok.begin(), ok.end());
+                if (ok == key) {
+                    if (sc > score(o)) o = r;
+                    std::sort(v.begin(), v.end(), [](const RawRound& x, const RawRound& y) { return score(x) > score(y); });
+                    return;
+                }
+            }
+            v.push_back(r);
+            std::sort(v.begin(), v.end(), [](const RawRound& x, const RawRound& y) { return score(x) > score(y); });
+            if (v.size() > K) v.pop_back();
+        }
+    };
+    auto collect_rounds = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cd, bool with_split, bool with_unb, Pool& pool) {
+        std::vector<int> tq;
+        for (int q = 0; q < nq; ++q)
+            if ((rp.tmask >> q) & 1) tq.push_back(q);
+        const int tn = (int)tq.size();
+        std::vector<int> ex;
+        auto finish = [&](RawRound& r) {
+            r.reverse = g[rp.gate_idx[r.cidx[0]]].reverse;
+            std::sort(r.cidx.begin(), r.cidx.end());
+        };
+        {
+            const int nr = std::min(RB, tn);
+            std::vector<int> idx(nr);
+            for (int k = 0; k < nr; ++k) idx[k] = k;
+            while (true) {
+                uint64_t rm = 0;
+                for (int k = 0; k < nr; ++k) rm |= 1ull << tq[idx[k]];
+                round_closure(g, rp.gate_idx, cd, rm, ex);
+                if (2 * (int)ex.size() > pool.floor_score()) {
+                    RawRound r;
+                    r.rmask = rm;
+                    r.cidx = ex;
+                    finish(r);
+                    pool.add(r);
+                }
+                int k = nr - 1;
+                while (k >= 0 && idx[k] == tn - nr + k) --k;
+                if (k < 0) break;
+                ++idx[k];
+                for (int m = k + 1; m < nr; ++m) idx[m] = idx[m - 1] + 1;
+            }
+        }
+        if (!with_split || tn < RS) return;
+        const int Hmin = with_unb ? std::max(1, std::min(cfg.split_min_left, RS / 2)) : RS / 2;
+        std::vector<int> idx(RS);
+        for (int k = 0; k < RS; ++k) idx[k] = k;
+        while (true) {
+            uint64_t sm = 0;
+            for (int k = 0; k < RS; ++k) sm |= 1ull << tq[idx[k]];
+            for (int H = RS / 2; H >= Hmin; --H) {
+                std::vector<int> sub(H);
+                for (int k = 0; k < H; ++k) sub[k] = k;
+                while (true) {
+                    if (!(2 * H == RS && sub[0] != 0)) {
+                        uint64_t lm = 0;
+                        for (int k = 0; k < H; ++k) lm |= 1ull << tq[idx[sub[k]]];
+                        split_closure(g, rp.gate_idx, cd, lm, sm & ~lm, false, ex);
+                        if (2 * (int)ex.size() - 1 > pool.floor_score()) {
+                            RawRound r;
+                            r.rmask = sm;
+                            r.lmask = lm;
+                            r.split = true;
+                            r.cidx = ex;
+                            finish(r);
+                            pool.add(r);
+                        }
+                    }
+                    int k = H - 1;
+                    while (k >= 0 && sub[k] == RS - H + k) --k;
+                    if (k < 0) break;
+                    ++sub[k];
+                    for (int m = k + 1; m < H; ++m) sub[m] = sub[m - 1] + 1;
+                }
+            }
+            int k = RS - 1;
+            while (k >= 0 && idx[k] == tn - RS + k) --k;
+            if (k < 0) break;
+            ++idx[k];
+            for (int m = k + 1; m < RS; ++m) idx[m] = idx[m - 1] + 1;
+        }
+    };
+
     std::vector<std::vector<char>> cdone(P);
     std::vector<RawRound> last_round(P), first_round(P);
     std::vector<char> single_round(P, 0);
     for (int p = 0; p < P; ++p) cdone[p].assign(raw[p].gate_idx.size(), 0);
+    // identical passes (same tile, same gate pattern, same store constraint) recur in every sweep of a
+    // high-order formula: their round decomposition is computed once
+    struct RoundsMemo {
+        RawRound last;
+        std::vector<RawRound> front;
+    };
+    std::map<std::string, RoundsMemo> memo;
+    auto memo_key = [&](int p) {
+        const RawPass& rp = raw[p];
+        const std::vector<Gate>& g = sg[rp.seg];
+        std::ostringstream os;
+        const uint64_t shared_next = rp.tmask & next_tile(p);
+        os << rp.tmask << ':' << shared_next << ':' << (rp.has_phase ? 1 : 0) << ':';
+        const int s0 = rp.gate_idx.empty() ? 0 : g[rp.gate_idx[0]].sweep;
+        for (int k : rp.gate_idx) os << g[k].i << ',' << g[k].j << ',' << (g[k].reverse ? 1 : 0) << ',' << (g[k].sweep - s0) << ';';
+        return os.str();
+    };
     // (a) last rounds
     for (int p = 0; p < P; ++p) {
         const RawPass& rp = raw[p];
         const std::vector<Gate>& g = sg[rp.seg];
+        const std::string key = memo_key(p);
+        auto it = memo.find(key);
+        if (it != memo.end()) {
+            last_round[p] = it->second.last;
+            rr[p] = it->second.front;
+            rlast[p] = last_round[p].rmask;
+            for (int c : last_round[p].cidx) cdone[p][c] = 1;
+            for (auto& r : rr[p])
+                for (int c : r.cidx) cdone[p][c] = 1;
+            if (rr[p].empty()) {
+                single_round[p] = 1;
+                rfirst[p] = rlast[p];
+            } else {
+                rfirst[p] = rr[p][0].rmask;
+                first_round[p] = rr[p][0];
+            }
+            continue;
+        }
         const uint64_t shared_next = rp.tmask & next_tile(p);
         const int s = popc(shared_next);
         RawRound best;
@@ -528,43 +662,68 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         for (int c : best.cidx) cdone[p][c] = 1;
         rlast[p] = best.rmask;
         last_round[p] = best;
-    }
-    // (b) first rounds, (c) middle rounds
-    for (int p = 0; p < P; ++p) {
-        const RawPass& rp = raw[p];
-        const std::vector<Gate>& g = sg[rp.seg];
-        size_t ndone = last_round[p].cidx.size();
-        if (ndone == rp.gate_idx.size()) {
+
+        // (b) first and middle rounds: beam search for the fewest rounds (breadth first over the round count,
+        // cfg.beam_width states kept per depth, cfg.beam_cands candidate rounds expanded per state)
+        size_t ndone0 = best.cidx.size();
+        if (ndone0 == rp.gate_idx.size()) {
             single_round[p] = 1;
             rfirst[p] = rlast[p];
+            memo[key] = RoundsMemo{last_round[p], {}};
             continue;
         }
-        const int pm = prev_index(p);
-        const bool hinted = pm < 0 && !cfg.cyclic && cfg.prev_tile_hint;
-        const uint64_t shared_prev = pm < 0 ? (hinted ? (rp.tmask & cfg.prev_tile_hint) : 0) : (rp.tmask & raw[pm].tmask);
-        const uint64_t rl_prev = pm < 0 ? (hinted ? cfg.prev_rlast_hint : 0) : rlast[pm];
-        // the first round is unconstrained: its tile arrives by bulk copies in the segmented arrival layout
-        // (xyk_kernels.cuh, arrival_stride_bytes) whose conflict-free lane positions the layout step provides
-        (void)shared_prev;
-        (void)rl_prev;
-        RawRound best;
-        allow_split = can_split && !rp.has_phase;  // the fused phase multiplies whole complex amplitudes
-        search_round(rp, g, cdone[p], false, 0, 99, 0, best);
-        allow_split = can_split;
-        if (best.cidx.empty()) throw std::runtime_error("compile_plan: first-round search made no progress");
-        for (int c : best.cidx) cdone[p][c] = 1;
-        ndone += best.cidx.size();
-        rfirst[p] = best.rmask;
-        first_round[p] = best;
-        rr[p].push_back(best);
-        while (ndone < rp.gate_idx.size()) {
-            RawRound mid;
-            search_round(rp, g, cdone[p], false, 0, 99, 0, mid);
-            if (mid.cidx.empty()) throw std::runtime_error("compile_plan: round search made no progress");
-            for (int c : mid.cidx) cdone[p][c] = 1;
-            ndone += mid.cidx.size();
-            rr[p].push_back(mid);
+        struct State {
+            std::vector<char> cd;
+            std::vector<RawRound> rounds;
+            size_t ndone;
+            int nsplit;
+        };
+        std::vector<State> beam;
+        beam.push_back(State{cdone[p], {}, ndone0, 0});
+        const size_t total = rp.gate_idx.size();
+        const int W = std::max(1, cfg.beam_width), KC = std::max(1, cfg.beam_cands);
+        bool finished = false;
+        State winner;
+        for (int depth = 0; !finished; ++depth) {
+            if (depth > 64) throw std::runtime_error("compile_plan: round search does not terminate");
+            std::vector<State> next;
+            for (const State& st : beam) {
+                Pool pool{(size_t)KC, {}};
+                const bool with_split = can_split && !(depth == 0 && rp.has_phase);  // the fused phase multiplies whole complex amplitudes
+                collect_rounds(rp, g, st.cd, with_split, depth > 0 || cfg.unb_first, pool);
+                if (pool.v.empty()) throw std::runtime_error("compile_plan: round search made no progress");
+                for (const RawRound& r : pool.v) {
+                    State ns = st;
+                    for (int c : r.cidx) ns.cd[c] = 1;
+                    ns.ndone += r.cidx.size();
+                    ns.nsplit += r.split ? 1 : 0;
+                    ns.rounds.push_back(r);
+                    next.push_back(std::move(ns));
+                }
+            }
+            std::stable_sort(next.begin(), next.end(), [](const State& x, const State& y) {
+                if (x.ndone != y.ndone) return x.ndone > y.ndone;
+                return x.nsplit < y.nsplit;
+            });
+            if (next.front().ndone == total) {
+                winner = next.front();
+                finished = true;
+                break;
+            }
+            beam.clear();
+            for (State& ns : next) {
+                bool dup = false;
+                for (const State& o : beam)
+                    if (o.cd == ns.cd) dup = true;
+                if (!dup) beam.push_back(std::move(ns));
+                if ((int)beam.size() >= W) break;
+            }
         }
+        rr[p] = winner.rounds;
+        cdone[p] = winner.cd;
+        rfirst[p] = rr[p][0].rmask;
+        first_round[p] = rr[p][0];
+        memo[key] = RoundsMemo{last_round[p], rr[p]};
     }
     for (int p = 0; p < P; ++p) rr[p].push_back(last_round[p]);
 
@@ -861,6 +1020,9 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 const size_t cnt = std::min((size_t)cfg.max_rounds, total - off);
                 PlanPass piece = pp;
                 piece.rounds.assign(pp.rounds.begin() + off, pp.rounds.begin() + off + cnt);
+                // the piece's store reads the whole tile out of shared memory: block-wide barrier after its last
+                // round, whatever the barrier towards the next round of the unsplit pass was
+                piece.rounds.back().cta_sync_after = 1;
                 piece.has_phase = pp.has_phase && off == 0;
                 piece.fuse_load = pp.fuse_load && off == 0;
                 piece.fuse_store = pp.fuse_store && off + cnt == total;
