@@ -731,7 +731,10 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // order: qubits shared with the previous tile that neither the previous last round nor this
     // first round holds in registers (-> lanes of the fused global I/O), then the other shared
     // qubits, then the remaining tile qubits, then everything else; ascending inside each class.
-    auto make_layout = [&](int p, std::vector<int>& perm, int& nshared, int& nfree) {
+    // `prev_layout` (positions of the qubits before the previous pass, empty if unknown): the three qubits that land on
+    // output bits 0..2 of the previous pass are the low lane bits of its last round's fused store, and that round READS them
+    // from shared-memory positions prev_layout[q]; three different bank classes there make those reads conflict free.
+    auto make_layout = [&](int p, std::vector<int>& perm, int& nshared, int& nfree, const std::vector<int>& prev_layout) {
         const uint64_t tile = raw[p].tmask;
         const int pm = prev_index(p);
         const bool hinted = pm < 0 && !cfg.cyclic && cfg.prev_tile_hint;
@@ -749,15 +752,45 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         const uint64_t rest = tile & ~shared;
         const uint64_t classes[6] = {shared & ~rl_prev & ~rfirst[p], shared & ~rl_prev & rfirst[p], shared & rl_prev & rfirst[p],
                                      shared & rl_prev & ~rfirst[p], rest & rfirst[p], rest & ~rfirst[p]};
+        uint64_t placed = 0;
+        if (!prev_layout.empty() && pm >= 0 && c_lane == 3) {
+            // candidates in preference order (class 0 first), pick the first triple of pairwise different bank classes
+            std::vector<int> cand;
+            for (int c = 0; c < 2; ++c)
+                for (int q = 0; q < nq; ++q)
+                    if ((classes[c] >> q) & 1) cand.push_back(q);
+            const int nc = (int)cand.size();
+            int best[3] = {-1, -1, -1};
+            for (int a = 0; a < nc && best[0] < 0; ++a)
+                for (int b = a + 1; b < nc && best[0] < 0; ++b)
+                    for (int c = b + 1; c < nc && best[0] < 0; ++c) {
+                        const int ca = lane_class(prev_layout[cand[a]]), cb = lane_class(prev_layout[cand[b]]), cc = lane_class(prev_layout[cand[c]]);
+                        if (ca != cb && ca != cc && cb != cc) {
+                            best[0] = cand[a];
+                            best[1] = cand[b];
+                            best[2] = cand[c];
+                        }
+                    }
+            if (best[0] >= 0)
+                for (int k = 0; k < 3; ++k) {
+                    perm[best[k]] = pos++;
+                    placed |= 1ull << best[k];
+                }
+        }
         for (uint64_t cls : classes)
             for (int q = 0; q < nq; ++q)
-                if ((cls >> q) & 1) perm[q] = pos++;
+                if (((cls & ~placed) >> q) & 1) perm[q] = pos++;
         for (int q = 0; q < nq; ++q)
             if (!((tile >> q) & 1)) perm[q] = pos++;
     };
     std::vector<std::vector<int>> layouts(P + 1);
     std::vector<int> nshared(P + 1, 0), nfree(P + 1, 0);
-    for (int p = 0; p < P; ++p) make_layout(p, layouts[p], nshared[p], nfree[p]);
+    {
+        const std::vector<int> none;
+        for (int p = 0; p < P; ++p) make_layout(p, layouts[p], nshared[p], nfree[p], p > 0 ? layouts[p - 1] : none);
+        if (cfg.cyclic && P > 1)  // the first layout follows the last pass: second sweep with the wrap-around known
+            for (int p = 0; p < P; ++p) make_layout(p, layouts[p], nshared[p], nfree[p], layouts[p > 0 ? p - 1 : P - 1]);
+    }
     if (P > 0 && cfg.cyclic) {
         layouts[P] = layouts[0];
         nshared[P] = nshared[0];
@@ -883,20 +916,54 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 std::sort(cand.begin(), cand.end(), [&](int a, int b) { return layouts[p + 1][a] < layouts[p + 1][b]; });
                 for (int k = 0; k < (int)cand.size() - nwarpbits; ++k) forced[nrounds - 1] |= 1ull << cand[k];
             }
+            // a choice W of warp qubits is good for round r when the lanes it leaves (tile minus registers minus W) still
+            // cover the three bank classes of the padded tile layout; rounds whose lane order is dictated by the fused
+            // global load / store are exempt
+            auto lanes_ok = [&](int r, uint64_t W) {
+                if ((r == 0 && fl) || (r == nrounds - 1 && fs)) return true;
+                int seen = 0;
+                for (int q = 0; q < nq; ++q)
+                    if (((rp.tmask & ~rr[p][r].rmask & ~W) >> q) & 1) seen |= 1 << lane_class(qpos[q]);
+                return seen == 7;
+            };
+            auto pick_w = [&](uint64_t X, int ra, int rb, bool& good) -> uint64_t {
+                std::vector<int> xs;
+                for (int q = nq - 1; q >= 0; --q)
+                    if ((X >> q) & 1) xs.push_back(q);  // highest-numbered first (deterministic)
+                uint64_t fallback = 0;
+                for (int q : xs)
+                    if (popc(fallback) < nwarpbits) fallback |= 1ull << q;
+                good = false;
+                if (nwarpbits != 2) return fallback;
+                for (size_t a = 0; a < xs.size(); ++a)
+                    for (size_t b = a + 1; b < xs.size(); ++b) {
+                        const uint64_t W = (1ull << xs[a]) | (1ull << xs[b]);
+                        bool ok = true;
+                        for (int r = ra; r <= rb && ok; ++r) ok = lanes_ok(r, W);
+                        if (ok) {
+                            good = true;
+                            return W;
+                        }
+                    }
+                return fallback;
+            };
             int r0 = 0;
             while (r0 < nrounds && nwarpbits > 0) {
                 uint64_t X = rp.tmask & ~rr[p][r0].rmask & ~forced[r0];
+                bool good = false;
+                uint64_t W = pick_w(X, r0, r0, good);
                 int r1 = r0;
                 while (r1 + 1 < nrounds) {
                     const uint64_t X2 = X & ~rr[p][r1 + 1].rmask & ~forced[r1 + 1];
                     if (popc(X2) < nwarpbits) break;
+                    bool good2 = false;
+                    const uint64_t W2 = pick_w(X2, r0, r1 + 1, good2);
+                    if (good && !good2) break;  // extending the run would cost a bank conflict: take the block-wide barrier instead
                     X = X2;
+                    W = W2;
+                    good = good2;
                     ++r1;
                 }
-                // keep the highest-numbered candidates (arbitrary but deterministic)
-                uint64_t W = 0;
-                for (int q = nq - 1; q >= 0 && popc(W) < nwarpbits; --q)
-                    if ((X >> q) & 1) W |= 1ull << q;
                 for (int r = r0; r <= r1; ++r) wsel[r] = W;
                 r0 = r1 + 1;
             }
