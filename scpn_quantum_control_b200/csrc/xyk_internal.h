@@ -98,6 +98,8 @@ struct SchedConfig {
     int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
     bool split_rounds = true;  // allow split rounds (RB + 1 register qubits over two real half-states)
+    int tile_beam = 1;         // tile search: sequences kept per depth (1 with tile_seeds = 1: greedy)
+    int tile_seeds = 1;        // tile search: seed gates tried per state
     int beam_width = 3;        // round search: states kept per depth (1 = greedy)
     int beam_cands = 3;        // round search: candidate rounds expanded per state
     bool unb_first = true, unb_last = true;  // unbalanced split rounds allowed as the first / last round of a pass

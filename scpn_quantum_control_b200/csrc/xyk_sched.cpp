@@ -219,9 +219,9 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // has to share qubits with the first one (cyclic programs), the late ones are free to become the
     // lane bits of the fused global I/O between the two passes
     std::vector<int> first_use(nq, 1 << 30);
-    auto grow_tile = [&](const std::vector<Gate>& g, const std::vector<char>& done, int first,
+    auto grow_tile = [&](const std::vector<Gate>& g, const std::vector<char>& done, int first, int seed,
                          uint64_t prev, uint64_t firstTile, int need_prev, int need_first) -> uint64_t {
-        uint64_t T = (1ull << g[first].i) | (1ull << g[first].j);
+        uint64_t T = (1ull << g[seed].i) | (1ull << g[seed].j);
         std::vector<int> ex;
         while (popc(T) < TB) {
             const int slots = TB - popc(T);
@@ -258,27 +258,126 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
 
     uint64_t prev_tile = 0, first_tile = 0;
     const int need = std::min(cfg.need_shared, TB);
+    // Tile sequence of a segment: breadth-first beam search over the pass count.  A state expands into one tile per
+    // seed gate (the first cfg.tile_seeds gates that are ready, i.e. first in line for both their qubits), each grown
+    // greedily from its seed; cfg.tile_beam states with the most gates done survive a depth.  Width 1 with one seed is
+    // the plain greedy sequence.  Segments with the same gate pattern entered from the same tile reuse the result.
+    struct TileState {
+        std::vector<char> done;
+        size_t ndone = 0;
+        uint64_t prev = 0;
+        std::vector<RawPass> passes;
+    };
+    struct TileMemo {
+        std::vector<uint64_t> tiles;
+    };
+    std::map<std::string, TileMemo> tile_memo;
+    size_t last_seg_with_gates = 0;
+    for (size_t s = 0; s < segs.size(); ++s)
+        if (!sg[s].empty()) last_seg_with_gates = s;
     for (size_t s = 0; s < segs.size(); ++s) {
         const std::vector<Gate>& g = sg[s];
         if (g.empty()) continue;
-        std::vector<char> done(g.size(), 0);
-        size_t ndone = 0;
-        bool first_of_seg = true;
-        int first = 0;
-        while (ndone < g.size()) {
-            while (done[first]) ++first;
-            uint64_t T = grow_tile(g, done, first, prev_tile, 0, need, 0);
-            RawPass rp;
+        auto make_pass = [&](const std::vector<char>& done, int first, uint64_t T, bool phase, RawPass& rp) {
             rp.tmask = T;
             rp.seg = (int)s;
-            rp.has_phase = first_of_seg;
+            rp.has_phase = phase;
             closure(g, done, first, T, rp.gate_idx);
-            if (rp.gate_idx.empty()) throw std::runtime_error("compile_plan: no progress");
-            for (int k : rp.gate_idx) done[k] = 1;
-            ndone += rp.gate_idx.size();
-            first_of_seg = false;
-            if (!first_tile) first_tile = T;
-            prev_tile = T;
+        };
+        std::string key;
+        {
+            std::ostringstream os;
+            os << prev_tile << ':' << (s == last_seg_with_gates ? first_tile : 0) << ':';
+            const int s0 = g[0].sweep;
+            for (const Gate& q : g) os << q.i << ',' << q.j << ',' << (q.sweep - s0) << ';';
+            key = os.str();
+        }
+        std::vector<RawPass> chosen;
+        auto mit = tile_memo.find(key);
+        if (mit != tile_memo.end()) {
+            std::vector<char> done(g.size(), 0);
+            int first = 0;
+            bool phase = true;
+            for (uint64_t T : mit->second.tiles) {
+                while (done[first]) ++first;
+                RawPass rp;
+                make_pass(done, first, T, phase, rp);
+                for (int k : rp.gate_idx) done[k] = 1;
+                phase = false;
+                chosen.push_back(std::move(rp));
+            }
+        } else {
+            std::vector<TileState> beam(1);
+            beam[0].done.assign(g.size(), 0);
+            beam[0].prev = prev_tile;
+            const int W = std::max(1, cfg.tile_beam), NS = std::max(1, cfg.tile_seeds);
+            bool finished = false;
+            for (int depth = 0; !finished; ++depth) {
+                if (depth > (int)g.size() + 1) throw std::runtime_error("compile_plan: tile search does not terminate");
+                std::vector<TileState> next;
+                for (const TileState& st : beam) {
+                    int first = 0;
+                    while (st.done[first]) ++first;
+                    // seeds: gates first in line for both their qubits (the first undone gate is always one)
+                    std::vector<int> seeds;
+                    {
+                        uint64_t seen = 0;
+                        for (int k = first; k < (int)g.size() && (int)seeds.size() < NS; ++k) {
+                            if (st.done[k]) continue;
+                            const uint64_t m = (1ull << g[k].i) | (1ull << g[k].j);
+                            if (!(m & seen)) seeds.push_back(k);
+                            seen |= m;
+                            if (seen == all_mask) break;
+                        }
+                    }
+                    std::vector<uint64_t> tried;
+                    for (int seed : seeds) {
+                        const uint64_t T = grow_tile(g, st.done, first, seed, st.prev, 0, need, 0);
+                        if (std::find(tried.begin(), tried.end(), T) != tried.end()) continue;
+                        tried.push_back(T);
+                        RawPass rp;
+                        make_pass(st.done, first, T, depth == 0, rp);
+                        if (rp.gate_idx.empty()) continue;
+                        TileState ns = st;
+                        for (int k : rp.gate_idx) ns.done[k] = 1;
+                        ns.ndone += rp.gate_idx.size();
+                        ns.prev = T;
+                        ns.passes.push_back(std::move(rp));
+                        next.push_back(std::move(ns));
+                    }
+                }
+                if (next.empty()) throw std::runtime_error("compile_plan: no progress");
+                // complete sequences: prefer one whose last tile already shares enough qubits with the program's first tile
+                int pick = -1;
+                for (int k = 0; k < (int)next.size(); ++k)
+                    if (next[k].ndone == g.size()) {
+                        const uint64_t ft = first_tile ? first_tile : next[k].passes[0].tmask;
+                        const bool closes = !(cfg.cyclic && s == last_seg_with_gates) || popc(next[k].prev & ft) >= std::min(need, popc(ft));
+                        if (pick < 0 || closes) pick = k;
+                        if (closes) break;
+                    }
+                if (pick >= 0) {
+                    chosen = std::move(next[pick].passes);
+                    finished = true;
+                    break;
+                }
+                std::stable_sort(next.begin(), next.end(), [](const TileState& a, const TileState& b) { return a.ndone > b.ndone; });
+                beam.clear();
+                for (TileState& ns : next) {
+                    bool dup = false;
+                    for (const TileState& o : beam)
+                        if (o.prev == ns.prev && o.done == ns.done) dup = true;
+                    if (!dup) beam.push_back(std::move(ns));
+                    if ((int)beam.size() >= W) break;
+                }
+            }
+            TileMemo tm;
+            for (const RawPass& rp : chosen) tm.tiles.push_back(rp.tmask);
+            tile_memo[key] = std::move(tm);
+        }
+        for (RawPass& rp : chosen) {
+            if (!first_tile) first_tile = rp.tmask;
+            prev_tile = rp.tmask;
             raw.push_back(std::move(rp));
         }
     }
@@ -309,7 +408,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         int first = 0;
         while (ndone < g.size()) {
             while (done[first]) ++first;
-            uint64_t T = grow_tile(g, done, first, prev_tile, first_tile, need, std::min(need, popc(first_tile)));
+            uint64_t T = grow_tile(g, done, first, first, prev_tile, first_tile, need, std::min(need, popc(first_tile)));
             RawPass rp;
             rp.tmask = T;
             rp.seg = s;

@@ -70,3 +70,38 @@ def test_shared_low_bits_between_consecutive_tiles():
     plan = plan_describe(K, w, 0.1, 1, 1)
     for p in plan["passes"]:
         assert p["n_shared"] >= 3
+
+
+def test_unbalanced_split_rounds_and_piece_barriers():
+    """n=20, order 2: the plan uses 2|4 split rounds, a pass longer than the descriptor's round limit is cut
+    into pieces, and every pass (piece) ends with a block-wide barrier -- its store reads the whole tile.
+    (Regression: the piece boundary used to inherit a warp-level barrier from the unsplit pass.)"""
+    n = 20
+    K, w = oc.random_problem(n, 70 + n)
+    plan = _check(n, K, w, 0.1, 2, 1)
+    kinds = {(r["split"], r["nleft"]) for p in plan["passes"] for r in p["rounds"]}
+    assert (1, 2) in kinds and (1, 3) in kinds and (0, 0) in kinds
+    assert all(r["nleft"] in (2, 3) for p in plan["passes"] for r in p["rounds"] if r["split"])
+    for p in plan["passes"]:
+        assert len(p["rounds"]) <= 14
+        assert p["rounds"][-1]["cta_sync_after"] == 1
+        for r in p["rounds"]:
+            if r["split"]:  # every gate joins the left group with the right group
+                left, right = set(r["regq"][: r["nleft"]]), set(r["regq"][r["nleft"]:])
+                assert all((i in left) != (j in left) and (i in right) != (j in right) for i, j, _ in r["gates"])
+
+
+def test_bank_conflict_free_lane_bits():
+    """The three lowest lane bits of (almost) every round sit on tile positions of three different bank classes of the
+    padded shared-memory layout (position mod 3); n=30 all-to-all: at most one conflicted round per layer."""
+    n = 30
+    K, w = oc.random_problem(n, 20260730)
+    plan = plan_describe(K, w, 0.02, 1, 1)
+    bad = 0
+    for p in plan["passes"]:
+        for ri, r in enumerate(p["rounds"]):
+            if ri == 0 and p["fuse_load"]:
+                continue  # arrival layout: positions {b, 9 + b}
+            if len({pos % 3 for pos in r["thrpos"][:3]}) != 3:
+                bad += 1
+    assert bad <= 1
