@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <sstream>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -75,6 +76,12 @@ struct xyk_handle_s {
     std::vector<cudaEvent_t> pass_events;  // per-launch timing of the tile pass kernel
     // sharded execution state machine
     std::vector<ShardStep> shard_steps;
+    struct ShardCacheEntry {
+        std::vector<ShardStep> steps;
+        int gates = 0, rounds = 0, passes = 0;
+    };
+    std::map<std::string, ShardCacheEntry> shard_cache;  // compiled sharded programs by (problem, formula, sharding on entry)
+    int64_t shard_compiles = 0;
     size_t shard_pos = 0;
     bool exchange_pending = false;
     std::vector<int> ex_out, ex_in;
@@ -343,6 +350,7 @@ void apply_env(SchedConfig& cfg) {
     if (const char* e = std::getenv("XYK_TILE_BEAM")) cfg.tile_beam = std::atoi(e);
     if (const char* e = std::getenv("XYK_TILE_SEEDS")) cfg.tile_seeds = std::atoi(e);
     if (const char* e = std::getenv("XYK_BEAM")) cfg.beam_width = cfg.beam_cands = std::atoi(e);
+    if (const char* e = std::getenv("XYK_RESTORE_GLOBALS")) cfg.restore_globals = std::atoi(e) != 0;
     if (const char* e = std::getenv("XYK_FUSE_IO")) cfg.fuse_io = std::atoi(e) != 0;
     if (const char* e = std::getenv("XYK_UNB_FIRST")) cfg.unb_first = std::atoi(e) != 0;
     if (const char* e = std::getenv("XYK_UNB_LAST")) cfg.unb_last = std::atoi(e) != 0;
@@ -686,14 +694,36 @@ int run_shard_steps(xyk_handle h) {
     return XYK_OK;
 }
 
-int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1) {
+int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1, double delta, int order, int reps) {
     SchedConfig cfg;
     cfg.TB = kTB;
     cfg.RB = kRB;
     cfg.max_rounds = kMaxRounds;
     cfg.peer_exchange = h->peers_ready && h->peer_exchange_opt;
+    cfg.restore_globals = true;
     apply_env(cfg);
     cfg.split_min_left = std::max(cfg.split_min_left, 2);  // the pass kernel has no 1 | 5 rounds
+    // a sharded program depends on which logical qubit sits on which rank bit on entry; calls that start from
+    // the same sharding (every call, when the program restores it) reuse the compiled steps
+    std::string key;
+    {
+        std::ostringstream os;
+        os.precision(17);
+        os << h->problem_version << ':' << (h->fuse_phase ? 1 : 0) << ':' << (cfg.peer_exchange ? 1 : 0) << ':' << order << ':' << reps << ':' << delta;
+        for (int q : current_globals(h)) os << ':' << q;
+        key = os.str();
+    }
+    auto hit = h->shard_cache.find(key);
+    if (hit != h->shard_cache.end()) {
+        h->shard_steps = hit->second.steps;
+        h->shard_pos = 0;
+        h->stats.last_gates = hit->second.gates;
+        h->stats.last_rounds = hit->second.rounds;
+        h->stats.last_passes = hit->second.passes;
+        h->stats.last_layers1 = l1;
+        return XYK_OK;
+    }
+    h->shard_compiles++;
     std::vector<ShardOp> ops;
     try {
         ops = compile_sharded(h->n, current_globals(h), segs, cfg, nullptr);
@@ -746,6 +776,12 @@ int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1) {
     h->stats.last_rounds = rounds;
     h->stats.last_passes = passes;
     h->stats.last_layers1 = l1;
+    if (h->shard_cache.size() > 64) h->shard_cache.clear();
+    xyk_handle_s::ShardCacheEntry& ce = h->shard_cache[key];
+    ce.steps = h->shard_steps;
+    ce.gates = gates;
+    ce.rounds = rounds;
+    ce.passes = passes;
     return XYK_OK;
 }
 
@@ -867,6 +903,7 @@ int xyk_set_option(xyk_handle h, int option, int64_t value) {
         case 100:
             h->debug_mode = (int)value;
             h->programs.clear();
+    h->shard_cache.clear();
             return XYK_OK;
         default:
             return fail(h, XYK_ERR_INVALID, "unknown option");
@@ -882,6 +919,7 @@ int xyk_set_problem(xyk_handle h, const double* K, const double* omega) {
     h->have_problem = true;
     h->problem_version++;
     h->programs.clear();
+    h->shard_cache.clear();
     return XYK_OK;
 }
 
@@ -919,7 +957,7 @@ int xyk_apply_layers(xyk_handle h, double delta, int order, int reps) {
         XYK_CHECK(h, !h->exchange_pending && h->shard_steps.empty(), XYK_ERR_STATE, "a sharded call is still in flight");
         int l1s = 0;
         std::vector<Segment> ssegs = build_sequence(h->pairs, delta, order, reps, &l1s);
-        int rcs = build_shard_steps(h, ssegs, l1s);
+        int rcs = build_shard_steps(h, ssegs, l1s, delta, order, reps);
         if (rcs) return rcs;
         return run_shard_steps(h);
     }
@@ -1283,6 +1321,7 @@ int64_t xyk_plan_describe(int n_local, int dtype, const double* K, const double*
             std::vector<int> glob;
             for (int q = n_local; q < n; ++q) glob.push_back(q);
             cfg.peer_exchange = (dtype & 2) != 0;  // test hook: bit 1 of `dtype` selects fused (peer-store) exchanges
+            cfg.restore_globals = (dtype & 4) != 0;  //            bit 2: end with the sharding the program started from
             js = sharded_to_json(compile_sharded(n, glob, segs, cfg, nullptr));
         } else {
             Plan plan = compile_plan(n_local, segs, cfg);

@@ -109,6 +109,7 @@ struct SchedConfig {
                                // (it moves the same bytes with twice as many shared-memory instructions)
     bool cyclic = true;    // the program ends in its own start layout (it can be replayed back to back)
     bool peer_exchange = false;  // sharded: fuse exchanges into the preceding pass (needs mapped peer buffers)
+    bool restore_globals = false;  // sharded: end every call with the sharding it started from (program reuse)
     std::vector<int> final_top;  // non-cyclic: qubits that must end on the highest physical bits, in this order
     // open programs chained across an exchange that is fused into the last pass's store:
     uint64_t next_tile_hint = 0;        // qubits (local indices) of the NEXT program's first tile that are local here

@@ -1284,7 +1284,22 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
                 ch.exchange_after = true;
             }
             if (ch.has_work) first = false;
+            // restore: after the very last gates the qubits that were sharded on entry go back to the rank bits, so
+            // that the next call finds the same sharding and reuses this program (one more exchange per call)
+            bool restored = false;
+            if (seg_finished && cfg_in.restore_globals && s + 1 == segs.size() && glob != global_qubits) {
+                bool feasible = true;
+                for (int q : global_qubits)
+                    for (int x : glob) feasible = feasible && (x != q);
+                if (feasible) {
+                    ch.outgoing = global_qubits;
+                    ch.incoming = glob;
+                    ch.exchange_after = true;
+                    restored = true;
+                }
+            }
             if (ch.has_work || ch.exchange_after) chunks.push_back(ch);
+            if (restored) glob = global_qubits;
             if (seg_finished) break;
             glob = ch.outgoing;  // rank bit k now carries outgoing[k]
         }

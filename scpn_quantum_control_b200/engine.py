@@ -198,7 +198,7 @@ def device_memory(device: int = 0) -> tuple[int, int]:
 
 
 def plan_describe(K: np.ndarray, omega: np.ndarray, delta: float, order: int, reps: int, n_local: int | None = None,
-                  peer_exchange: bool = False) -> dict:
+                  peer_exchange: bool = False, restore_sharding: bool = False) -> dict:
     """Host-only: the pass program the schedule compiler emits (no GPU needed).  With ``n_local < n`` the
     sharded program (local programs separated by / fused with exchanges) is returned."""
     lib = _lib.load()
@@ -206,7 +206,7 @@ def plan_describe(K: np.ndarray, omega: np.ndarray, delta: float, order: int, re
     omega = np.ascontiguousarray(omega, dtype=np.float64)
     n = omega.shape[0]
     nl = n if n_local is None else n_local
-    flag = 2 if peer_exchange else 0
+    flag = (2 if peer_exchange else 0) | (4 if restore_sharding else 0)
     need = lib.xyk_plan_describe(nl, flag, _dptr(K), _dptr(omega), n, float(delta), order, reps, None, 0)
     if need < 0:
         raise RuntimeError(_lib.last_error(None))

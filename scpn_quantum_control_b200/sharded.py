@@ -158,12 +158,17 @@ class ShardedXYKEngine:
         tot = self._allreduce(np.concatenate([ex, ey]))
         ex, ey = tot[: self.n].copy(), tot[self.n:].copy()
         if glob:
+            lay = self.eng.layout()
+            entry = sorted(glob, key=lambda q: lay[q])  # rank bit k carried entry[k]
             self.bring_local(glob)
             ex2, ey2 = self.eng.xy_expectations()
             tot2 = self._allreduce(np.concatenate([ex2, ey2]))
             for q in glob:
                 ex[q] = tot2[q]
                 ey[q] = tot2[self.n + q]
+            # back to the sharding found on entry: the evolution reuses the program compiled for it
+            arr = (c_int * self.g)(*entry)
+            self._drive(self.eng._check(self.eng._lib.xyk_begin_exchange(self.eng._h, arr)))
         return ex, ey
 
     def order_parameter(self) -> tuple[float, float]:

@@ -63,6 +63,21 @@ def main():
             ok &= bool(good)
             summary["checks"].append({"order": order, "reps": reps, "infidelity": infid, "dR": dR, "norm2": nrm,
                                       "sumZ_err": abs(zsum - zref), "ok": bool(good)})
+    # program reuse: every call ends with the sharding it started from, and so does an R(t) evaluation
+    eng.init_product_state()
+    g0 = eng.global_qubits()
+    eng.apply_layers(0.1, 1, 1)
+    g1 = eng.global_qubits()
+    R1, _ = eng.order_parameter()
+    g2 = eng.global_qubits()
+    eng.apply_layers(0.1, 1, 1)
+    R2, _ = eng.order_parameter()
+    if rank == 0:
+        ref = c_oracle_evolve(n, K, w, 0.2, 2, 1)
+        dR = abs(R2 - oc.order_parameter(ref, n)[0])
+        good = g0 == g1 == g2 and dR < 1e-9
+        ok &= bool(good)
+        summary["checks"].append({"sharding_restored": g0 == g1 == g2, "dR_two_calls": dR, "ok": bool(good)})
     # echo: forward L layers, then the inverse sequence = order-2 layers with negative time are exact inverses
     eng.init_product_state()
     eng.apply_layers(0.2, 2, 2)

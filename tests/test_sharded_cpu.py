@@ -36,6 +36,27 @@ def test_sharded_program_matches_reference_order(n, g, order, peer):
         assert n_fused > 0, "no exchange was fused into a pass"
 
 
+@pytest.mark.parametrize("peer", [False, True])
+@pytest.mark.parametrize("n,g", [(14, 1), (16, 3)])
+def test_sharded_program_restores_its_sharding(n, g, peer):
+    """With restore_sharding the program ends with the qubits that were sharded on entry back on their rank bits
+    (one more exchange), so that the engine can replay the compiled program layer after layer."""
+    K, w = oc.random_problem(n, 900 + n + g)
+    Kc, wc = oc.canonicalise(n, K, w)
+    prog = plan_describe(Kc, wc, 0.1, 1, 1, n_local=n - g, peer_exchange=peer, restore_sharding=True)
+    z, p = oc.term_list(Kc, wc)
+    psi0 = oc.initial_state(wc)
+    ref = oc.evolve_product_formula(psi0.copy(), z, p, 0.1, 1, 1)
+    got, perm, n_ex, n_fused = simulate_sharded(prog, n, n - g, psi0, wc)
+    assert [perm[q] for q in range(n - g, n)] == list(range(n - g, n)), "sharded qubits did not return to their rank bits"
+    inv = [0] * n
+    for q in range(n):
+        inv[perm[q]] = q
+    back = permute_bits(got, n, inv)
+    assert 1.0 - oc.fidelity(back, ref) < 1e-12
+    assert n_ex + n_fused >= 3
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
