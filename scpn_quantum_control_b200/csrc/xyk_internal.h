@@ -98,6 +98,7 @@ struct SchedConfig {
     int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
     bool split_rounds = true;  // allow split rounds (RB + 1 register qubits over two real half-states)
+    int tile_groups = 100;       // > 0: cost-guided beam (this width) over tiles made of index triples (cyclic programs)
     int tile_beam = 1;         // tile search: sequences kept per depth (1 with tile_seeds = 1: greedy)
     int tile_seeds = 1;        // tile search: seed gates tried per state
     int beam_width = 3;        // round search: states kept per depth (1 = greedy)

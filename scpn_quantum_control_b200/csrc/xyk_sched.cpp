@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 
@@ -161,6 +162,15 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     plan.nq = nq;
     plan.TB = TB;
     plan.RB = RB;
+    std::string cfg_sig;  // everything of the configuration the memoised searches depend on
+    {
+        std::ostringstream os;
+        os << nq << '/' << TB << '/' << RB << '/' << cfg.need_shared << '/' << cfg.lane_bits << '/' << cfg.fuse_io << cfg.split_rounds << cfg.cyclic
+           << cfg.unb_first << cfg.unb_last << '/' << cfg.split_margin << '/' << cfg.split_min_left << '/' << cfg.beam_width << '/' << cfg.beam_cands << '/'
+           << cfg.tile_groups << '/' << cfg.tile_beam << '/' << cfg.tile_seeds << '/' << cfg.next_tile_hint << '/' << cfg.prev_tile_hint << '/'
+           << cfg.prev_rlast_hint << '/' << cfg.final_positions.size() << '/' << cfg.final_top.size() << '|';
+        cfg_sig = os.str();
+    }
 
     // ---- 1. choose the tile (set of TB logical qubits) of every pass, segment by segment ----
     struct RawPass {
@@ -271,7 +281,11 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     struct TileMemo {
         std::vector<uint64_t> tiles;
     };
-    std::map<std::string, TileMemo> tile_memo;
+    // process-wide: the same gate pattern (another step size, another handle) reuses the searched tile sequence
+    static std::map<std::string, TileMemo> tile_memo;
+    static std::mutex tile_memo_mutex;
+    std::lock_guard<std::mutex> tile_memo_lock(tile_memo_mutex);
+    if (tile_memo.size() > 4096) tile_memo.clear();
     size_t last_seg_with_gates = 0;
     for (size_t s = 0; s < segs.size(); ++s)
         if (!sg[s].empty()) last_seg_with_gates = s;
@@ -287,7 +301,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         std::string key;
         {
             std::ostringstream os;
-            os << prev_tile << ':' << (s == last_seg_with_gates ? first_tile : 0) << ':';
+            os << cfg_sig << prev_tile << ':' << (s == last_seg_with_gates ? first_tile : 0) << ':';
             const int s0 = g[0].sweep;
             for (const Gate& q : g) os << q.i << ',' << q.j << ',' << (q.sweep - s0) << ';';
             key = os.str();
@@ -306,6 +320,129 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 phase = false;
                 chosen.push_back(std::move(rp));
             }
+        } else if (cfg.tile_groups > 0 && cfg.cyclic && nq > TB && cfg.final_positions.empty()) {
+            // Cost-guided beam over tile sequences.  Candidate tiles: unions of TB / 3 groups of three consecutive qubit
+            // indices (the natural blocks of a lexicographic sweep) that share >= `need` qubits with the previous tile,
+            // plus the greedy tile.  A pass is priced with the measured model of the pass kernel:
+            //   max(floor, 0.6 + 1.14 R + 0.05 G) ms, R ~ number of group-pair blocks touched, G gates,
+            //   floor = 5.7 ms (+1.2 ms when only three qubits are shared: 128-byte store chunks).
+            const int ngroups = (nq + 2) / 3, per_tile = TB / 3;
+            std::vector<uint64_t> gmask(ngroups, 0);
+            for (int q = 0; q < nq; ++q) gmask[q / 3] |= 1ull << q;
+            std::vector<uint64_t> cand_tiles;
+            {
+                std::vector<int> idx(per_tile);
+                for (int k = 0; k < per_tile; ++k) idx[k] = k;
+                if (ngroups >= per_tile)
+                    while (true) {
+                        uint64_t T = 0;
+                        for (int k = 0; k < per_tile; ++k) T |= gmask[idx[k]];
+                        cand_tiles.push_back(T);
+                        int k = per_tile - 1;
+                        while (k >= 0 && idx[k] == ngroups - per_tile + k) --k;
+                        if (k < 0) break;
+                        ++idx[k];
+                        for (int m = k + 1; m < per_tile; ++m) idx[m] = idx[m - 1] + 1;
+                    }
+            }
+            struct CState {
+                std::vector<char> done;
+                size_t ndone = 0;
+                uint64_t prev = 0;
+                double cost = 0.0;
+                std::vector<uint64_t> tiles;
+            };
+            auto pass_cost = [&](const std::vector<int>& gate_idx, int shared, bool has_prev) {
+                std::vector<char> blk((size_t)ngroups * ngroups, 0);
+                int R = 0;
+                for (int k : gate_idx) {
+                    const int a = g[k].i / 3, b = g[k].j / 3;
+                    char& c = blk[(size_t)a * ngroups + b];
+                    if (!c) {
+                        c = 1;
+                        ++R;
+                    }
+                }
+                const double body = 0.6 + 1.14 * R + 0.05 * (double)gate_idx.size();
+                const double floor = 5.7 + ((has_prev && shared < 4) ? 1.2 : 0.0);
+                return std::max(body, floor);
+            };
+            const int W = std::max(1, cfg.tile_groups);
+            const double lambda = 0.24;  // ms of credit per executed gate when ranking partial sequences
+            std::vector<CState> beam(1);
+            beam[0].done.assign(g.size(), 0);
+            beam[0].prev = prev_tile;
+            CState best_full;
+            bool have_full = false;
+            std::vector<int> ex;
+            for (int depth = 0; depth < 4 * (int)g.size() && !beam.empty(); ++depth) {
+                std::vector<CState> next;
+                for (const CState& st : beam) {
+                    if (have_full && st.cost + 5.7 >= best_full.cost) continue;  // cannot beat the best complete sequence
+                    int first = 0;
+                    while (st.done[first]) ++first;
+                    std::vector<uint64_t> tiles_here;
+                    tiles_here.push_back(grow_tile(g, st.done, first, first, st.prev, 0, need, 0));
+                    for (uint64_t T : cand_tiles)
+                        if (!st.prev || popc(T & st.prev) >= std::min(need, popc(st.prev))) tiles_here.push_back(T);
+                    for (size_t ti = 0; ti < tiles_here.size(); ++ti) {
+                        const uint64_t T = tiles_here[ti];
+                        if (ti > 0 && T == tiles_here[0]) continue;
+                        closure(g, st.done, first, T, ex);
+                        if (ex.empty()) continue;
+                        CState ns;
+                        ns.done = st.done;
+                        for (int k : ex) ns.done[k] = 1;
+                        ns.ndone = st.ndone + ex.size();
+                        ns.prev = T;
+                        ns.cost = st.cost + pass_cost(ex, st.prev ? popc(T & st.prev) : TB, st.prev != 0);
+                        ns.tiles = st.tiles;
+                        ns.tiles.push_back(T);
+                        if (ns.ndone == g.size()) {
+                            // closing the cycle: a last tile that does not share enough with the program's first tile costs a pass
+                            const uint64_t ft = first_tile ? first_tile : ns.tiles[0];
+                            if (s == last_seg_with_gates && popc(T & ft) < std::min(need, popc(ft))) ns.cost += 5.7;
+                            if (!have_full || ns.cost < best_full.cost) {
+                                best_full = ns;
+                                have_full = true;
+                            }
+                        } else {
+                            next.push_back(std::move(ns));
+                        }
+                    }
+                }
+                std::sort(next.begin(), next.end(), [&](const CState& a, const CState& b) {
+                    return a.cost - lambda * (double)a.ndone < b.cost - lambda * (double)b.ndone;
+                });
+                beam.clear();
+                for (CState& ns : next) {
+                    bool dup = false;
+                    for (const CState& o : beam)
+                        if (o.prev == ns.prev && o.ndone == ns.ndone && o.done == ns.done) {
+                            dup = true;
+                            break;
+                        }
+                    if (!dup) beam.push_back(std::move(ns));
+                    if ((int)beam.size() >= W) break;
+                }
+            }
+            if (!have_full) throw std::runtime_error("compile_plan: tile search found no complete sequence");
+            {
+                std::vector<char> done(g.size(), 0);
+                int first = 0;
+                bool phase = true;
+                for (uint64_t T : best_full.tiles) {
+                    while (done[first]) ++first;
+                    RawPass rp;
+                    make_pass(done, first, T, phase, rp);
+                    for (int k : rp.gate_idx) done[k] = 1;
+                    phase = false;
+                    chosen.push_back(std::move(rp));
+                }
+            }
+            TileMemo tm;
+            tm.tiles = best_full.tiles;
+            tile_memo[key] = std::move(tm);
         } else {
             std::vector<TileState> beam(1);
             beam[0].done.assign(g.size(), 0);
@@ -709,13 +846,14 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         RawRound last;
         std::vector<RawRound> front;
     };
-    std::map<std::string, RoundsMemo> memo;
+    static std::map<std::string, RoundsMemo> memo;  // process-wide, like the tile memo (the caller holds its lock)
+    if (memo.size() > 16384) memo.clear();
     auto memo_key = [&](int p) {
         const RawPass& rp = raw[p];
         const std::vector<Gate>& g = sg[rp.seg];
         std::ostringstream os;
         const uint64_t shared_next = rp.tmask & next_tile(p);
-        os << rp.tmask << ':' << shared_next << ':' << (rp.has_phase ? 1 : 0) << ':';
+        os << cfg_sig << rp.tmask << ':' << shared_next << ':' << (rp.has_phase ? 1 : 0) << ':';
         const int s0 = rp.gate_idx.empty() ? 0 : g[rp.gate_idx[0]].sweep;
         for (int k : rp.gate_idx) os << g[k].i << ',' << g[k].j << ',' << (g[k].reverse ? 1 : 0) << ',' << (g[k].sweep - s0) << ';';
         return os.str();
