@@ -282,7 +282,10 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
     const PlanRound& last = pp.rounds.back();
     const int last_nreg = last.split ? kRB + 1 : kRB;
     for (int b = 0; b < kTB - last_nreg; ++b) d.last_thr_out[b] = (uint8_t)pp.out_of_in[last.thrpos[b]];
-    for (int k = 0; k < last_nreg; ++k) d.last_reg_out[k] = (uint8_t)pp.out_of_in[last.regpos[k]];
+    for (int k = 0; k < last_nreg; ++k) {
+        d.last_reg_out[k] = (uint8_t)pp.out_of_in[last.regpos[k]];
+        d.st_reg_idx[k] = pp.out_of_in[last.regpos[k]] < 32 ? (1u << pp.out_of_in[last.regpos[k]]) : 0u;  // local index bits only (< 2^32 amplitudes)
+    }
     // fused diagonal phase: weights per INPUT physical bit, register table of round 0
     if (pp.has_phase && h->fuse_phase && !h->zterms.empty()) {
         d.flags |= kPassHasPhase;

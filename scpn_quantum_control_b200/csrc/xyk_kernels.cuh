@@ -410,6 +410,7 @@ struct PassDesc {
     uint8_t st_odst[16];     //                that output bit
     uint8_t last_thr_out[8]; // fused store: output bit of the qubit on thread bit b (split: b + 1) of the LAST round
     uint8_t last_reg_out[8]; //              output bit of the qubit on register bit k of the LAST round
+    uint32_t st_reg_idx[8];  // fused store: output INDEX stride (1 << output bit) of the LAST round's register bit k
     uint32_t arr_reg[8];     // fused load: byte stride of round 0's register bit k in the arrival layout (arrival_stride_bytes)
     uint64_t out_base;       // peer passes: output-index contribution of this device's rank bits
     double ph_const;         // fused phase: contribution of the sharded (rank) bits, constant on this device
@@ -1033,26 +1034,43 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                             split_global_store<2, RS, NV, PEER>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
                         }
                     } else if (split) {
-                        char* pb0 = pb + (half << 3);          // elements with f = 0: component `half`
-                        char* pb1 = pb + 8 - (half << 3);      // elements with f = 1: the other component
+                        // eight per-thread pointers over the three high register bits (component by their parity) and
+                        // eight warp-uniform 32-bit index offsets over the three low bits: one IMAD.WIDE per store
+                        double* q0 = reinterpret_cast<double*>(pb) + half;        // elements with f = 0: component `half`
+                        double* q1 = reinterpret_cast<double*>(pb) + (1u - half); // elements with f = 1: the other component
+                        double* bq[8];
+                        uint32_t lo2[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t hi = 0, l = 0;
+#pragma unroll
+                            for (int k = 0; k < HS; ++k) {
+                                if ((c >> k) & 1) hi += P.st_reg_idx[HS + k];
+                                if ((c >> k) & 1) l += P.st_reg_idx[k];
+                            }
+                            bq[c] = ((__builtin_popcount(c) & 1) ? q1 : q0) + 2ull * hi;
+                            lo2[c] = 2u * l;
+                        }
 #pragma unroll
                         for (int j = 0; j < NV; ++j) {
-                            uint64_t off = 0;
-#pragma unroll
-                            for (int k = 0; k < RS; ++k)
-                                if ((j >> k) & 1) off += 16ull << P.last_reg_out[k];
                             const bool fj = __builtin_popcount(j >> HS) & 1;
-                            __stcs(reinterpret_cast<double*>((fj ? pb1 : pb0) + off), fj ? flip_sign(v[j], smask) : v[j]);
+                            __stcs(bq[j >> HS] + lo2[j & ((1 << HS) - 1)], fj ? flip_sign(v[j], smask) : v[j]);
                         }
                     } else {
+                        double2* bq[8];
+                        uint32_t lo[4];
 #pragma unroll
-                        for (int j = 0; j < NREG; ++j) {
-                            uint64_t off = 0;
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t hi = 0;
 #pragma unroll
-                            for (int k = 0; k < RB; ++k)
-                                if ((j >> k) & 1) off += 16ull << P.last_reg_out[k];
-                            __stcs(reinterpret_cast<double2*>(pb + off), make_double2(v[2 * j], v[2 * j + 1]));
+                            for (int k = 0; k < 3; ++k)
+                                if ((c >> k) & 1) hi += P.st_reg_idx[2 + k];
+                            bq[c] = reinterpret_cast<double2*>(pb) + hi;
                         }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) lo[c] = ((c & 1) ? P.st_reg_idx[0] : 0u) + ((c & 2) ? P.st_reg_idx[1] : 0u);
+#pragma unroll
+                        for (int j = 0; j < NREG; ++j) __stcs(bq[j >> 2] + lo[j & 3], make_double2(v[2 * j], v[2 * j + 1]));
                     }
                 }
             } else {

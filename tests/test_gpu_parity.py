@@ -116,6 +116,48 @@ def test_tiled_equals_gate_by_gate_n24():
         assert 1.0 - oc.fidelity(pa, pb) < FID_TOL
 
 
+def test_full_size_n30_properties():
+    """BASELINE configs[3] at full size (16 GiB state), where no oracle reaches: norm and <sum Z> are conserved by
+    a first-order layer, and an order-2 step followed by the same step with negative time (its exact inverse, gate
+    by gate) returns the analytic product state: <Z_q> = cos(theta_q), <X_q> = sin(theta_q), <Y_q> = 0."""
+    from scpn_quantum_control_b200 import _lib
+
+    n = 30
+    lib = _lib.load()
+    import ctypes
+
+    free_b, total_b = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.xyk_device_memory(0, ctypes.byref(free_b), ctypes.byref(total_b)) == 0
+    if free_b.value < 40 * 2**30:
+        pytest.skip("needs 2 x 16 GiB of free device memory")
+    rng = np.random.default_rng(20260730)
+    A = rng.uniform(0.05, 1.0, (n, n))
+    K = (A + A.T) / 2.0
+    np.fill_diagonal(K, 0.0)
+    w = rng.uniform(0.5, 4.0, n)
+    th = np.mod(w, 2 * np.pi)
+    with XYKEngine(n) as e:
+        e.set_problem(K, w)
+        e.set_engine("tiled")
+        e.init_product_state()
+        e.apply_layers(0.02, 1, 1)
+        st = e.stats()
+        assert st["last_gates"] == n * (n - 1) // 2 and st["last_passes"] >= 2
+        assert abs(e.norm2() - 1.0) < 1e-10
+        assert abs(e.z_expectations().sum() - np.cos(th).sum()) < 1e-9
+        x1, _ = e.xy_expectations()
+        assert np.abs(x1 - np.sin(th)).max() > 1e-3  # the layer did something
+        e.init_product_state()
+        e.apply_layers(0.05, 2, 1)
+        e.apply_layers(-0.05, 2, 1)
+        x, y = e.xy_expectations()
+        z = e.z_expectations()
+        assert np.abs(x - np.sin(th)).max() < 1e-9
+        assert np.abs(y).max() < 1e-9
+        assert np.abs(z - np.cos(th)).max() < 1e-9
+        assert abs(e.norm2() - 1.0) < 1e-10
+
+
 @pytest.mark.parametrize("name", sorted(k for k, v in GOLD.items() if v["mode"] == "T"))
 def test_solver_run_vs_golden_trotter_traces(name):
     c = GOLD[name]
