@@ -350,6 +350,7 @@ void apply_env(SchedConfig& cfg) {
     if (const char* e = std::getenv("XYK_LANE_BITS")) cfg.lane_bits = std::atoi(e);
     if (const char* e = std::getenv("XYK_NEED_SHARED")) cfg.need_shared = std::atoi(e);
     if (const char* e = std::getenv("XYK_SPLIT")) cfg.split_rounds = std::atoi(e) != 0;
+    if (const char* e = std::getenv("XYK_TILE_GROUPS_OPEN")) cfg.tile_groups_open = std::atoi(e) != 0;
     if (const char* e = std::getenv("XYK_TILE_GROUPS")) cfg.tile_groups = std::atoi(e);
     if (const char* e = std::getenv("XYK_TILE_BEAM")) cfg.tile_beam = std::atoi(e);
     if (const char* e = std::getenv("XYK_TILE_SEEDS")) cfg.tile_seeds = std::atoi(e);

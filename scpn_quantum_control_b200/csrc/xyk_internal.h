@@ -99,6 +99,7 @@ struct SchedConfig {
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
     bool split_rounds = true;  // allow split rounds (RB + 1 register qubits over two real half-states)
     int tile_groups = 100;       // > 0: cost-guided beam (this width) over tiles made of index triples (cyclic programs)
+    bool tile_groups_open = true;  // ... also for the open (non-cyclic) local programs of a sharded state
     int tile_beam = 1;         // tile search: sequences kept per depth (1 with tile_seeds = 1: greedy)
     int tile_seeds = 1;        // tile search: seed gates tried per state
     int beam_width = 3;        // round search: states kept per depth (1 = greedy)

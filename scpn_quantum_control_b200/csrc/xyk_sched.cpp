@@ -167,7 +167,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         std::ostringstream os;
         os << nq << '/' << TB << '/' << RB << '/' << cfg.need_shared << '/' << cfg.lane_bits << '/' << cfg.fuse_io << cfg.split_rounds << cfg.cyclic
            << cfg.unb_first << cfg.unb_last << '/' << cfg.split_margin << '/' << cfg.split_min_left << '/' << cfg.beam_width << '/' << cfg.beam_cands << '/'
-           << cfg.tile_groups << '/' << cfg.tile_beam << '/' << cfg.tile_seeds << '/' << cfg.next_tile_hint << '/' << cfg.prev_tile_hint << '/'
+           << cfg.tile_groups << cfg.tile_groups_open << '/' << cfg.tile_beam << '/' << cfg.tile_seeds << '/' << cfg.next_tile_hint << '/' << cfg.prev_tile_hint << '/'
            << cfg.prev_rlast_hint << '/' << cfg.final_positions.size() << '/' << cfg.final_top.size() << '|';
         cfg_sig = os.str();
     }
@@ -301,7 +301,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         std::string key;
         {
             std::ostringstream os;
-            os << cfg_sig << prev_tile << ':' << (s == last_seg_with_gates ? first_tile : 0) << ':';
+            os << cfg_sig << prev_tile << ':' << (s == last_seg_with_gates ? (cfg.cyclic ? first_tile : cfg.next_tile_hint) : 0) << ':';
             const int s0 = g[0].sweep;
             for (const Gate& q : g) os << q.i << ',' << q.j << ',' << (q.sweep - s0) << ';';
             key = os.str();
@@ -320,11 +320,11 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 phase = false;
                 chosen.push_back(std::move(rp));
             }
-        } else if (cfg.tile_groups > 0 && cfg.cyclic && nq > TB && cfg.final_positions.empty()) {
+        } else if (cfg.tile_groups > 0 && nq > TB && (cfg.cyclic || cfg.tile_groups_open)) {
             // Cost-guided beam over tile sequences.  Candidate tiles: unions of TB / 3 groups of three consecutive qubit
             // indices (the natural blocks of a lexicographic sweep) that share >= `need` qubits with the previous tile,
             // plus the greedy tile.  A pass is priced with the measured model of the pass kernel:
-            //   max(floor, 0.6 + 1.14 R + 0.05 G) ms, R ~ number of group-pair blocks touched, G gates,
+            //   max(floor, 0.6 + 1.14 R + 0.05 G) ms, R ~ estimated rounds, G gates,
             //   floor = 5.7 ms (+1.2 ms when only three qubits are shared: 128-byte store chunks).
             const int ngroups = (nq + 2) / 3, per_tile = TB / 3;
             std::vector<uint64_t> gmask(ngroups, 0);
@@ -353,16 +353,12 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                 std::vector<uint64_t> tiles;
             };
             auto pass_cost = [&](const std::vector<int>& gate_idx, int shared, bool has_prev) {
-                std::vector<char> blk((size_t)ngroups * ngroups, 0);
-                int R = 0;
-                for (int k : gate_idx) {
-                    const int a = g[k].i / 3, b = g[k].j / 3;
-                    char& c = blk[(size_t)a * ngroups + b];
-                    if (!c) {
-                        c = 1;
-                        ++R;
-                    }
-                }
+                // rounds: nine gates per split round at best, plus one round per two index triples with internal gates
+                // (a triangle never fits a split round)
+                uint64_t tri = 0;
+                for (int k : gate_idx)
+                    if (g[k].i / 3 == g[k].j / 3) tri |= 1ull << (g[k].i / 3);
+                const int R = ((int)gate_idx.size() + 8) / 9 + (popc(tri) + 1) / 2;
                 const double body = 0.6 + 1.14 * R + 0.05 * (double)gate_idx.size();
                 const double floor = 5.7 + ((has_prev && shared < 4) ? 1.2 : 0.0);
                 return std::max(body, floor);
@@ -400,8 +396,9 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                         ns.tiles.push_back(T);
                         if (ns.ndone == g.size()) {
                             // closing the cycle: a last tile that does not share enough with the program's first tile costs a pass
-                            const uint64_t ft = first_tile ? first_tile : ns.tiles[0];
-                            if (s == last_seg_with_gates && popc(T & ft) < std::min(need, popc(ft))) ns.cost += 5.7;
+                            // (open programs chained to a next one: its first tile, as far as it is local here)
+                            const uint64_t ft = cfg.cyclic ? (first_tile ? first_tile : ns.tiles[0]) : cfg.next_tile_hint;
+                            if (ft && s == last_seg_with_gates && popc(T & ft) < std::min(need, popc(ft))) ns.cost += 5.7;
                             if (!have_full || ns.cost < best_full.cost) {
                                 best_full = ns;
                                 have_full = true;
@@ -424,6 +421,32 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
                         }
                     if (!dup) beam.push_back(std::move(ns));
                     if ((int)beam.size() >= W) break;
+                }
+            }
+            {
+                // the plain greedy sequence priced with the same model: the beam's ranking can prune it away
+                CState gs;
+                gs.done.assign(g.size(), 0);
+                gs.prev = prev_tile;
+                int first = 0;
+                while (gs.ndone < g.size()) {
+                    while (gs.done[first]) ++first;
+                    const uint64_t T = grow_tile(g, gs.done, first, first, gs.prev, 0, need, 0);
+                    closure(g, gs.done, first, T, ex);
+                    if (ex.empty()) break;
+                    for (int k : ex) gs.done[k] = 1;
+                    gs.ndone += ex.size();
+                    gs.cost += pass_cost(ex, gs.prev ? popc(T & gs.prev) : TB, gs.prev != 0);
+                    gs.prev = T;
+                    gs.tiles.push_back(T);
+                }
+                if (gs.ndone == g.size()) {
+                    const uint64_t ft = cfg.cyclic ? (first_tile ? first_tile : gs.tiles[0]) : cfg.next_tile_hint;
+                    if (ft && s == last_seg_with_gates && popc(gs.prev & ft) < std::min(need, popc(ft))) gs.cost += 5.7;
+                    if (!have_full || gs.cost < best_full.cost) {
+                        best_full = gs;
+                        have_full = true;
+                    }
                 }
             }
             if (!have_full) throw std::runtime_error("compile_plan: tile search found no complete sequence");
