@@ -389,7 +389,6 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
     cfg.RB = kRB;
     cfg.max_rounds = kMaxRounds;
     apply_env(cfg);
-    cfg.split_min_left = std::max(cfg.split_min_left, 2);  // the pass kernel has no 1 | 5 rounds
     prog->plan = compile_plan(h->nlocal, segs, cfg);
     prog->plan.layers1_equiv = l1;
     prog->loc2log.resize(h->nlocal);
@@ -400,30 +399,31 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
     return prog;
 }
 
-// the eight instantiations of the pass kernel: shear-form rotations or not, peer (fused exchange) stores or not,
-// unbalanced (2 | 4) split rounds compiled in or not (the lean kernel is ~30 % smaller)
+// the twelve instantiations of the pass kernel: shear-form rotations or not, peer (fused exchange) stores or not,
+// and which unbalanced split round is compiled in: none (the lean kernel, ~30 % smaller), 2 | 4, or 1 | 5
 using PassKernel = void (*)(const double2*, double2*, const Desc, uint64_t, const PeerPtrs);
-PassKernel pass_kernel_fn(bool lift, bool peer, bool unb) {
-    if (lift) {
-        if (peer) return unb ? tile_pass_kernel<kTB, kRB, true, 3, true, true> : tile_pass_kernel<kTB, kRB, true, 3, true, false>;
-        return unb ? tile_pass_kernel<kTB, kRB, true, 3, false, true> : tile_pass_kernel<kTB, kRB, true, 3, false, false>;
-    }
-    if (peer) return unb ? tile_pass_kernel<kTB, kRB, false, 3, true, true> : tile_pass_kernel<kTB, kRB, false, 3, true, false>;
-    return unb ? tile_pass_kernel<kTB, kRB, false, 3, false, true> : tile_pass_kernel<kTB, kRB, false, 3, false, false>;
+template <int UNB>
+PassKernel pass_kernel_unb(bool lift, bool peer) {
+    if (lift) return peer ? tile_pass_kernel<kTB, kRB, true, 3, true, UNB> : tile_pass_kernel<kTB, kRB, true, 3, false, UNB>;
+    return peer ? tile_pass_kernel<kTB, kRB, false, 3, true, UNB> : tile_pass_kernel<kTB, kRB, false, 3, false, UNB>;
 }
-bool desc_unbalanced(const Desc& d) {
-    static const bool force = std::getenv("XYK_FORCE_UNB") != nullptr;  // experiment: always run the larger kernel
-    if (force) return true;
+PassKernel pass_kernel_fn(bool lift, bool peer, int unb) {
+    return unb == 2 ? pass_kernel_unb<2>(lift, peer) : (unb == 1 ? pass_kernel_unb<1>(lift, peer) : pass_kernel_unb<0>(lift, peer));
+}
+// 0: balanced rounds only; 1 / 2: the pass holds 1 | 5 / 2 | 4 split rounds (the schedule compiler never mixes the two)
+int desc_unbalanced(const Desc& d) {
+    static const char* force = std::getenv("XYK_FORCE_UNB");  // experiment: always run one of the larger kernels
+    int kind = force ? std::atoi(force) : 0;
     for (int r = 0; r < d.nrounds; ++r)
-        if (d.rounds[r].split == 2) return true;
-    return false;
+        if (d.rounds[r].split == 1 || d.rounds[r].split == 2) kind = d.rounds[r].split;
+    return kind;
 }
 
 int configure_pass_kernels(xyk_handle h) {
     const int smem = (int)tile_bytes<kTB>();
-    for (int k = 0; k < 8; ++k) XYK_CUDA(h, cudaFuncSetAttribute(pass_kernel_fn(k & 1, k & 2, k & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int k = 0; k < 12; ++k) XYK_CUDA(h, cudaFuncSetAttribute(pass_kernel_fn(k & 1, k & 2, k >> 2), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
-    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel_fn(true, false, false), 1 << (kTB - kRB), smem));
+    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel_fn(true, false, 0), 1 << (kTB - kRB), smem));
     if (occ < 1) occ = 1;
     h->pass_grid = occ * h->sm_count;
     return XYK_OK;
@@ -707,7 +707,6 @@ int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1, do
     cfg.peer_exchange = h->peers_ready && h->peer_exchange_opt;
     cfg.restore_globals = true;
     apply_env(cfg);
-    cfg.split_min_left = std::max(cfg.split_min_left, 2);  // the pass kernel has no 1 | 5 rounds
     // a sharded program depends on which logical qubit sits on which rank bit on entry; calls that start from
     // the same sharding (every call, when the program restores it) reuse the compiled steps
     std::string key;

@@ -105,8 +105,8 @@ struct SchedConfig {
     int beam_width = 3;        // round search: states kept per depth (1 = greedy)
     int beam_cands = 3;        // round search: candidate rounds expanded per state
     bool unb_first = true, unb_last = true;  // unbalanced split rounds allowed as the first / last round of a pass
-    int split_min_left = 2;    // smallest left group of a split round: 3 = balanced 3 | 3 only, 2 adds 2 | 4 (1 | 5 is
-                               // understood by the compiler but has no kernel: its code made ptxas spill)
+    int split_min_left = 1;    // smallest left group of a split round: 3 = balanced 3 | 3 only, 2 adds 2 | 4, 1 adds 1 | 5
+                               // (a pass uses one unbalanced kind only: each has its own kernel instantiation)
     int split_margin = 1;      // a split round must run at least this many more gates than the best complex round
                                // (it moves the same bytes with twice as many shared-memory instructions)
     bool cyclic = true;    // the program ends in its own start layout (it can be replayed back to back)

@@ -396,7 +396,7 @@ struct PassDesc {
         uint16_t regsw[8];   // shared-memory byte stride of register bit k: 16 * pad_slot(1 << regpos[k])
         uint32_t mask;       // enabled pair slots
         uint16_t cta_sync;   // 1: block-wide barrier after this round's exchange; 0: warp-level barrier suffices
-        uint16_t split;      // 0: complex round; 2, 3: split round (RB + 1 register qubits, one real component per amplitude;
+        uint16_t split;      // 0: complex round; 1, 2, 3: split round (RB + 1 register qubits, one real component per amplitude;
                              // see PlanRound) whose left group has that many qubits (the right group sits on the high register bits)
         double ca[NSLOT];    // shear form: -tan(phi/2); standard form: cos(phi)
         double cb[NSLOT];    // sin(phi)
@@ -666,7 +666,7 @@ __device__ __forceinline__ void split_global_store(const double (&v)[NV], double
     }
 }
 
-template <int TB, int RB, bool LIFT, int MINB, bool PEER, bool UNB>
+template <int TB, int RB, bool LIFT, int MINB, bool PEER, int UNB>
 __global__ void __launch_bounds__(1 << (TB - RB), MINB)
 tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                  const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles, const __grid_constant__ PeerPtrs peers) {
@@ -812,7 +812,8 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             rb[5] = hdr.z >> 16;
             const uint32_t nl = (hdr.w >> 17) & 3u;  // 0: complex round; else the left-group size of a split round
             const bool split = nl != 0u;
-            const bool unb = UNB && nl == 2u;  // unbalanced (2 | 4) split round: separate code, UNB kernels only
+            // unbalanced split round (UNB = 2: 2 | 4, UNB = 1: 1 | 5): separate code, present only in the kernel instantiation for it
+            const bool unb = UNB != 0 && nl == (uint32_t)UNB;
             const uint32_t boff1 = boff + 8u - (half << 4);  // split rounds: base of the elements with f(j) = 1
             if ((flags & kPassPfLate) && !(flags & kPassFuseLoad) && r == nr - 1) prefetch_next();
             const Round& R = P.rounds[r];  // gate coefficients stay in the constant bank: a uniform operand of DFMA
@@ -829,7 +830,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     if constexpr (UNB) {
                         uint32_t st[RS];
                         for (int k = 0; k < RS; ++k) st[k] = P.arr_reg[k];
-                        split_exchange<2, RS, NV, false>(v, tile_u32 + lin0 + (half << 3), half, st, smask);
+                        split_exchange<(UNB ? UNB : 2), RS, NV, false>(v, tile_u32 + lin0 + (half << 3), half, st, smask);
                     }
                 } else if (split) {
                     const uint32_t p0 = tile_u32 + lin0 + (half << 3);
@@ -886,7 +887,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 // offset of the low register bits: LDS [R + UR], no per-access vector arithmetic
                 if (unb) {
                     if constexpr (UNB) {
-                        split_exchange<2, RS, NV, false>(v, boff, half, rb, smask);
+                        split_exchange<(UNB ? UNB : 2), RS, NV, false>(v, boff, half, rb, smask);
                     }
                 } else if (split) {
                     uint32_t bh[1 << HS], lo[1 << HS];
@@ -957,7 +958,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             const uint32_t mask = hdr.w & 0xffffu;
             if (unb) {
                 if constexpr (UNB) {
-                    split_gates<2, RS, NV, LIFT>(v, mask, R);
+                    split_gates<(UNB ? UNB : 2), RS, NV, LIFT>(v, mask, R);
                 }
             } else if (split) {
 #pragma unroll
@@ -1004,7 +1005,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 if constexpr (PEER) {
                     if (unb) {
                         if constexpr (UNB) {
-                            split_global_store<2, RS, NV, PEER>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
+                            split_global_store<(UNB ? UNB : 2), RS, NV, PEER>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
                         }
                     } else if (split) {
 #pragma unroll
@@ -1031,7 +1032,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     char* pb = reinterpret_cast<char*>(out) + (dbase << 4);
                     if (unb) {
                         if constexpr (UNB) {
-                            split_global_store<2, RS, NV, PEER>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
+                            split_global_store<(UNB ? UNB : 2), RS, NV, PEER>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
                         }
                     } else if (split) {
                         // eight per-thread pointers over the three high register bits (component by their parity) and
@@ -1081,7 +1082,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 if (r == 0 && (flags & kPassFuseLoad)) __syncthreads();
                 if (unb) {
                     if constexpr (UNB) {
-                        split_exchange<2, RS, NV, true>(v, boff, half, rb, smask);
+                        split_exchange<(UNB ? UNB : 2), RS, NV, true>(v, boff, half, rb, smask);
                     }
                 } else if (split) {
                     uint32_t bh[1 << HS], lo[1 << HS];

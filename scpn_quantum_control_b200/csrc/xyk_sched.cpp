@@ -658,6 +658,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             if (popc(both & ~blocked) < 2) break;
         }
     };
+    int cur_unb_kind = 0;  // left-group size of the unbalanced split rounds the searches may use right now (0: none)
     auto search_split = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cdone, bool reverse_scan,
                             uint64_t limit_mask, int limit, uint64_t prefer, RawRound& best) {
         std::vector<int> tq;
@@ -669,8 +670,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         best.cidx.clear();
         best.split = true;
         if (tn < RS) return;
-        // left-group sizes: RS/2 | RS/2 always; down to cfg.split_min_left also the unbalanced bipartitions (2 | RS-2, 1 | RS-1)
-        const int Hmin = cfg.unb_last ? std::max(1, std::min(cfg.split_min_left, RS / 2)) : RS / 2;  // search_split serves the last rounds
+        // left-group sizes: RS/2 | RS/2 always, plus the unbalanced bipartition of the kind being tried (2 | RS-2 or 1 | RS-1)
+        const int Hunb = cfg.unb_last ? cur_unb_kind : 0;  // search_split serves the last rounds
         std::vector<int> idx(RS), ex;
         for (int k = 0; k < RS; ++k) idx[k] = k;
         int best_pref = -1;
@@ -678,7 +679,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             uint64_t sm = 0;
             for (int k = 0; k < RS; ++k) sm |= 1ull << tq[idx[k]];
             if (popc(sm & limit_mask) <= limit) {
-                for (int H = RS / 2; H >= Hmin; --H) {
+                for (int H : {RS / 2, Hunb}) {
+                    if (H <= 0) continue;
                     std::vector<int> sub(H);
                     for (int k = 0; k < H; ++k) sub[k] = k;
                     while (true) {
@@ -820,13 +822,14 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             }
         }
         if (!with_split || tn < RS) return;
-        const int Hmin = with_unb ? std::max(1, std::min(cfg.split_min_left, RS / 2)) : RS / 2;
+        const int Hunb = with_unb ? cur_unb_kind : 0;
         std::vector<int> idx(RS);
         for (int k = 0; k < RS; ++k) idx[k] = k;
         while (true) {
             uint64_t sm = 0;
             for (int k = 0; k < RS; ++k) sm |= 1ull << tq[idx[k]];
-            for (int H = RS / 2; H >= Hmin; --H) {
+            for (int H : {RS / 2, Hunb}) {
+                if (H <= 0) continue;
                 std::vector<int> sub(H);
                 for (int k = 0; k < H; ++k) sub[k] = k;
                 while (true) {
@@ -903,86 +906,116 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             }
             continue;
         }
-        const uint64_t shared_next = rp.tmask & next_tile(p);
-        const int s = popc(shared_next);
-        RawRound best;
-        // fused store: the c_lane lowest output bits must carry shared qubits that this round keeps on lanes;
-        // every other shared qubit may sit in registers (the next pass's bulk tile load does not care)
-        if (cfg.fuse_io && s - c_lane >= 0) search_round(rp, g, cdone[p], true, shared_next, s - c_lane, 0, best);
-        if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
-        if (best.cidx.empty()) throw std::runtime_error("compile_plan: last-round search made no progress");
-        if (best.split && best.cidx.size() == rp.gate_idx.size() && rp.has_phase) {
-            // a single round that also carries the diagonal phase must hold whole complex amplitudes
-            allow_split = false;
-            best = RawRound();
+        // one decomposition per admissible kind of unbalanced split round (none / 2 | 4 / 1 | 5: a pass never mixes the
+        // two, each lives in its own kernel instantiation); the fewest rounds win, ties go to the leaner kernel
+        auto decompose = [&]() {
+            cdone[p].assign(rp.gate_idx.size(), 0);
+            rr[p].clear();
+            const uint64_t shared_next = rp.tmask & next_tile(p);
+            const int s = popc(shared_next);
+            RawRound best;
+            // fused store: the c_lane lowest output bits must carry shared qubits that this round keeps on lanes;
+            // every other shared qubit may sit in registers (the next pass's bulk tile load does not care)
             if (cfg.fuse_io && s - c_lane >= 0) search_round(rp, g, cdone[p], true, shared_next, s - c_lane, 0, best);
             if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
-            allow_split = can_split;
-        }
-        for (int c : best.cidx) cdone[p][c] = 1;
-        rlast[p] = best.rmask;
-        last_round[p] = best;
+            if (best.cidx.empty()) throw std::runtime_error("compile_plan: last-round search made no progress");
+            if (best.split && best.cidx.size() == rp.gate_idx.size() && rp.has_phase) {
+                // a single round that also carries the diagonal phase must hold whole complex amplitudes
+                allow_split = false;
+                best = RawRound();
+                if (cfg.fuse_io && s - c_lane >= 0) search_round(rp, g, cdone[p], true, shared_next, s - c_lane, 0, best);
+                if (best.cidx.empty()) search_round(rp, g, cdone[p], true, 0, 99, 0, best);
+                allow_split = can_split;
+            }
+            for (int c : best.cidx) cdone[p][c] = 1;
+            rlast[p] = best.rmask;
+            last_round[p] = best;
 
-        // (b) first and middle rounds: beam search for the fewest rounds (breadth first over the round count,
-        // cfg.beam_width states kept per depth, cfg.beam_cands candidate rounds expanded per state)
-        size_t ndone0 = best.cidx.size();
-        if (ndone0 == rp.gate_idx.size()) {
-            single_round[p] = 1;
-            rfirst[p] = rlast[p];
-            memo[key] = RoundsMemo{last_round[p], {}};
-            continue;
-        }
-        struct State {
-            std::vector<char> cd;
-            std::vector<RawRound> rounds;
-            size_t ndone;
-            int nsplit;
-        };
-        std::vector<State> beam;
-        beam.push_back(State{cdone[p], {}, ndone0, 0});
-        const size_t total = rp.gate_idx.size();
-        const int W = std::max(1, cfg.beam_width), KC = std::max(1, cfg.beam_cands);
-        bool finished = false;
-        State winner;
-        for (int depth = 0; !finished; ++depth) {
-            if (depth > 64) throw std::runtime_error("compile_plan: round search does not terminate");
-            std::vector<State> next;
-            for (const State& st : beam) {
-                Pool pool{(size_t)KC, {}};
-                const bool with_split = can_split && !(depth == 0 && rp.has_phase);  // the fused phase multiplies whole complex amplitudes
-                collect_rounds(rp, g, st.cd, with_split, depth > 0 || cfg.unb_first, pool);
-                if (pool.v.empty()) throw std::runtime_error("compile_plan: round search made no progress");
-                for (const RawRound& r : pool.v) {
-                    State ns = st;
-                    for (int c : r.cidx) ns.cd[c] = 1;
-                    ns.ndone += r.cidx.size();
-                    ns.nsplit += r.split ? 1 : 0;
-                    ns.rounds.push_back(r);
-                    next.push_back(std::move(ns));
+            // (b) first and middle rounds: beam search for the fewest rounds (breadth first over the round count,
+            // cfg.beam_width states kept per depth, cfg.beam_cands candidate rounds expanded per state)
+            size_t ndone0 = best.cidx.size();
+            if (ndone0 == rp.gate_idx.size()) {
+                rr[p].clear();
+                return;
+            }
+            struct State {
+                std::vector<char> cd;
+                std::vector<RawRound> rounds;
+                size_t ndone;
+                int nsplit;
+            };
+            std::vector<State> beam;
+            beam.push_back(State{cdone[p], {}, ndone0, 0});
+            const size_t total = rp.gate_idx.size();
+            const int W = std::max(1, cfg.beam_width), KC = std::max(1, cfg.beam_cands);
+            bool finished = false;
+            State winner;
+            for (int depth = 0; !finished; ++depth) {
+                if (depth > 64) throw std::runtime_error("compile_plan: round search does not terminate");
+                std::vector<State> next;
+                for (const State& st : beam) {
+                    Pool pool{(size_t)KC, {}};
+                    const bool with_split = can_split && !(depth == 0 && rp.has_phase);  // the fused phase multiplies whole complex amplitudes
+                    collect_rounds(rp, g, st.cd, with_split, depth > 0 || cfg.unb_first, pool);
+                    if (pool.v.empty()) throw std::runtime_error("compile_plan: round search made no progress");
+                    for (const RawRound& r : pool.v) {
+                        State ns = st;
+                        for (int c : r.cidx) ns.cd[c] = 1;
+                        ns.ndone += r.cidx.size();
+                        ns.nsplit += r.split ? 1 : 0;
+                        ns.rounds.push_back(r);
+                        next.push_back(std::move(ns));
+                    }
+                }
+                std::stable_sort(next.begin(), next.end(), [](const State& x, const State& y) {
+                    if (x.ndone != y.ndone) return x.ndone > y.ndone;
+                    return x.nsplit < y.nsplit;
+                });
+                if (next.front().ndone == total) {
+                    winner = next.front();
+                    finished = true;
+                    break;
+                }
+                beam.clear();
+                for (State& ns : next) {
+                    bool dup = false;
+                    for (const State& o : beam)
+                        if (o.cd == ns.cd) dup = true;
+                    if (!dup) beam.push_back(std::move(ns));
+                    if ((int)beam.size() >= W) break;
                 }
             }
-            std::stable_sort(next.begin(), next.end(), [](const State& x, const State& y) {
-                if (x.ndone != y.ndone) return x.ndone > y.ndone;
-                return x.nsplit < y.nsplit;
-            });
-            if (next.front().ndone == total) {
-                winner = next.front();
-                finished = true;
-                break;
-            }
-            beam.clear();
-            for (State& ns : next) {
-                bool dup = false;
-                for (const State& o : beam)
-                    if (o.cd == ns.cd) dup = true;
-                if (!dup) beam.push_back(std::move(ns));
-                if ((int)beam.size() >= W) break;
+            rr[p] = winner.rounds;
+            cdone[p] = winner.cd;
+            rfirst[p] = rr[p][0].rmask;
+            first_round[p] = rr[p][0];
+        };
+        std::vector<int> kinds{0};
+        if (can_split && cfg.split_min_left <= 2 && RS / 2 > 2) kinds.push_back(2);
+        if (can_split && cfg.split_min_left <= 1 && RS / 2 > 1) kinds.push_back(1);
+        RoundsMemo best_dec;
+        size_t best_n = 0;
+        for (int kind : kinds) {
+            cur_unb_kind = kind;
+            decompose();
+            const size_t nrd = rr[p].size() + 1;
+            if (best_n == 0 || nrd < best_n) {
+                best_n = nrd;
+                best_dec = RoundsMemo{last_round[p], rr[p]};
             }
         }
-        rr[p] = winner.rounds;
-        cdone[p] = winner.cd;
-        rfirst[p] = rr[p][0].rmask;
-        first_round[p] = rr[p][0];
+        cur_unb_kind = 0;
+        last_round[p] = best_dec.last;
+        rr[p] = best_dec.front;
+        rlast[p] = last_round[p].rmask;
+        cdone[p].assign(rp.gate_idx.size(), 1);
+        if (rr[p].empty()) {
+            single_round[p] = 1;
+            rfirst[p] = rlast[p];
+        } else {
+            rfirst[p] = rr[p][0].rmask;
+            first_round[p] = rr[p][0];
+        }
         memo[key] = RoundsMemo{last_round[p], rr[p]};
     }
     for (int p = 0; p < P; ++p) rr[p].push_back(last_round[p]);

@@ -73,16 +73,18 @@ def test_shared_low_bits_between_consecutive_tiles():
 
 
 def test_unbalanced_split_rounds_and_piece_barriers():
-    """n=20, order 2: the plan uses 2|4 split rounds, a pass longer than the descriptor's round limit is cut
+    """n=20, order 2: the plan uses unbalanced (2|4 or 1|5) split rounds, a pass longer than the descriptor's round limit is cut
     into pieces, and every pass (piece) ends with a block-wide barrier -- its store reads the whole tile.
     (Regression: the piece boundary used to inherit a warp-level barrier from the unsplit pass.)"""
     n = 20
     K, w = oc.random_problem(n, 70 + n)
     plan = _check(n, K, w, 0.1, 2, 1)
     kinds = {(r["split"], r["nleft"]) for p in plan["passes"] for r in p["rounds"]}
-    assert (1, 2) in kinds and (1, 3) in kinds and (0, 0) in kinds
-    assert all(r["nleft"] in (2, 3) for p in plan["passes"] for r in p["rounds"] if r["split"])
+    assert ((1, 2) in kinds or (1, 1) in kinds) and (1, 3) in kinds and (0, 0) in kinds
+    assert all(r["nleft"] in (1, 2, 3) for p in plan["passes"] for r in p["rounds"] if r["split"])
     for p in plan["passes"]:
+        # a pass never mixes 1|5 and 2|4 rounds (each kind has its own kernel instantiation)
+        assert len({r["nleft"] for r in p["rounds"] if r["split"] and r["nleft"] != 3}) <= 1
         assert len(p["rounds"]) <= 14
         assert p["rounds"][-1]["cta_sync_after"] == 1
         for r in p["rounds"]:
