@@ -102,8 +102,8 @@ struct SchedConfig {
     bool tile_groups_open = true;  // ... also for the open (non-cyclic) local programs of a sharded state
     int tile_beam = 1;         // tile search: sequences kept per depth (1 with tile_seeds = 1: greedy)
     int tile_seeds = 1;        // tile search: seed gates tried per state
-    int beam_width = 3;        // round search: states kept per depth (1 = greedy)
-    int beam_cands = 3;        // round search: candidate rounds expanded per state
+    int beam_width = 6;        // round search: states kept per depth (1 = greedy)
+    int beam_cands = 6;        // round search: candidate rounds expanded per state
     bool unb_first = true, unb_last = true;  // unbalanced split rounds allowed as the first / last round of a pass
     int split_min_left = 1;    // smallest left group of a split round: 3 = balanced 3 | 3 only, 2 adds 2 | 4, 1 adds 1 | 5
                                // (a pass uses one unbalanced kind only: each has its own kernel instantiation)
