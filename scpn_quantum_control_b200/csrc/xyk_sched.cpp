@@ -1424,6 +1424,7 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
         std::vector<int> outgoing, incoming;
     };
     std::vector<Chunk> chunks;
+    bool restored_at_end = false;
     for (size_t s = 0; s < segs.size(); ++s) {
         const std::vector<GateOp>& gs = segs[s].gates;
         std::vector<char> done(gs.size(), 0);
@@ -1490,6 +1491,7 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
                     ch.incoming = glob;
                     ch.exchange_after = true;
                     restored = true;
+                    restored_at_end = true;
                 }
             }
             if (ch.has_work || ch.exchange_after) chunks.push_back(ch);
@@ -1509,6 +1511,7 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
     // how each program was chained to its successor (needed when it is recompiled in step (2))
     std::vector<uint64_t> nop_next_hint(C, 0);
     std::vector<std::vector<int>> nop_final_positions(C), nop_final_top(C);
+    std::vector<uint64_t> nop_prev_hint(C, 0), nop_prev_rlast(C, 0);  // ... and to its predecessor
     // translate a mask over chunk a's local indices into chunk b's local indices (qubits local in both)
     auto translate = [&](uint64_t mask, const Chunk& a, const Chunk& b) -> uint64_t {
         uint64_t out = 0;
@@ -1559,6 +1562,8 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
             SchedConfig ncfg = base_cfg();
             ncfg.prev_tile_hint = translate(probe.last_tile_mask, ch, nx);
             ncfg.prev_rlast_hint = translate(probe.last_rlast_mask, ch, nx);
+            nop_prev_hint[c + 1] = ncfg.prev_tile_hint;
+            nop_prev_rlast[c + 1] = ncfg.prev_rlast_hint;
             // keep whatever chained the next program to ITS successor
             ncfg.next_tile_hint = nop_next_hint[c + 1];
             ncfg.final_positions = nop_final_positions[c + 1];
@@ -1589,6 +1594,62 @@ std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubit
         op.incoming_fused = ch.incoming;
         op.rank_out.clear();
         for (int k = 0; k < g; ++k) op.rank_out.push_back(nop.plan.start_perm[nx.log2loc[ch.incoming[k]]]);
+    }
+    // ---- the restoring exchange wraps around: fuse it into the last program's last pass, which then stores (with
+    // peer stores) straight into the START layout of the first program -- the next call begins without an exchange,
+    // without a staging sweep and without a re-layout ----
+    if (restored_at_end && cfg_in.fuse_io && cfg_in.peer_exchange && C >= 2) {
+        const int L = C - 1;
+        int F = -1;
+        for (int c = 0; c < C && F < 0; ++c)
+            if (chunks[c].has_work && !local_ops[c].plan.passes.empty()) F = c;
+        if (F >= 0 && F != L && chunks[L].has_work && chunks[L].exchange_after && !fused[L] && !chunks[L].sub.gates.empty() &&
+            !local_ops[L].plan.passes.empty()) {
+            Chunk& chF = chunks[F];
+            Chunk& chL = chunks[L];
+            // (a) the first program again, its start layout ordered around what the last program leaves low
+            SchedConfig fcfg = base_cfg();
+            fcfg.prev_tile_hint = translate(local_ops[L].plan.last_tile_mask, chL, chF);
+            fcfg.prev_rlast_hint = translate(local_ops[L].plan.last_rlast_mask, chL, chF);
+            fcfg.next_tile_hint = nop_next_hint[F];
+            fcfg.final_positions = nop_final_positions[F];
+            fcfg.final_top = nop_final_top[F];
+            std::vector<Segment> fseg{chF.sub};
+            Plan planF = compile_plan(nl, fseg, fcfg);
+            // (b) the last program again: its last pass writes that start layout, the restored qubits leave to the rank bits
+            SchedConfig lcfg = base_cfg();
+            lcfg.prev_tile_hint = nop_prev_hint[L];
+            lcfg.prev_rlast_hint = nop_prev_rlast[L];
+            lcfg.next_tile_hint = translate(planF.first_tile_mask, chF, chL);
+            lcfg.final_positions.assign(nl, -1);
+            bool ok = true;
+            for (int l = 0; l < nl; ++l) {
+                const int q = chL.loc2log[l];
+                int k = -1;
+                for (int x = 0; x < g; ++x)
+                    if (chL.outgoing[x] == q) k = x;
+                if (k >= 0) lcfg.final_positions[l] = nl + k;
+                else if (chF.log2loc[q] >= 0) lcfg.final_positions[l] = planF.start_perm[chF.log2loc[q]];
+                else ok = false;
+            }
+            for (int k = 0; k < g && ok; ++k) ok = chF.log2loc[chL.incoming[k]] >= 0;
+            if (ok) {
+                std::vector<Segment> lseg{chL.sub};
+                Plan planL = compile_plan(nl, lseg, lcfg);
+                // the program before the last one stores into the last program's start layout: it must not have moved
+                if (!planL.passes.empty() && planL.start_perm == local_ops[L].plan.start_perm) {
+                    local_ops[F].plan = std::move(planF);
+                    ShardOp& op = local_ops[L];
+                    op.plan = std::move(planL);
+                    op.peer_last = true;
+                    op.outgoing_fused = chL.outgoing;
+                    op.incoming_fused = chL.incoming;
+                    op.rank_out.clear();
+                    for (int k = 0; k < g; ++k) op.rank_out.push_back(local_ops[F].plan.start_perm[chF.log2loc[chL.incoming[k]]]);
+                    fused[L] = 1;
+                }
+            }
+        }
     }
     std::vector<ShardOp> ops;
     for (int c = 0; c < C; ++c) {
