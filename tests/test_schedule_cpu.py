@@ -107,3 +107,31 @@ def test_bank_conflict_free_lane_bits():
             if len({pos % 3 for pos in r["thrpos"][:3]}) != 3:
                 bad += 1
     assert bad <= 1
+
+
+def test_plan_invariants_headline_programs():
+    """Barrier kinds, warp-local rounds, phase round, split bipartitions, fused-store lanes (tests/plan_check.py)
+    of the programs the bench and the GPU tests run."""
+    from tests.plan_check import check_plan
+
+    for n, order, reps in ((30, 1, 1), (30, 2, 1), (24, 1, 2), (16, 6, 1), (13, 2, 2), (31, 1, 1)):
+        K, w = oc.random_problem(n, 20260700 + n)
+        check_plan(plan_describe(K, w, 0.02, order, reps))
+
+
+def test_random_sparse_couplings_plan_and_invariants():
+    """Irregular problems: random coupling graphs of several densities, some omega_i = 0, orders 1 and 2: the
+    compiled program reproduces the reference gate order (NumPy emulation) and keeps the structural invariants."""
+    from tests.plan_check import check_plan
+
+    rng = np.random.default_rng(12345)
+    for _ in range(16):
+        n = int(rng.integers(12, 16))
+        order, reps = int(rng.choice([1, 2])), int(rng.choice([1, 2]))
+        dens = float(rng.choice([0.15, 0.3, 0.6, 1.0]))
+        A = rng.uniform(0.05, 1.0, (n, n)) * (rng.random((n, n)) < dens)
+        K = (A + A.T) / 2.0
+        np.fill_diagonal(K, 0.0)
+        w = rng.uniform(0.5, 4.0, n)
+        w[rng.random(n) < 0.2] = 0.0
+        check_plan(_check(n, K, w, 0.1, order, reps))

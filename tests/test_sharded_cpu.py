@@ -103,3 +103,34 @@ def test_gloo_all_to_all_is_the_qubit_swap(tmp_path):
     swap[nl - 1], swap[nl] = nl, nl - 1
     want = permute_bits(full, n, swap)
     assert np.array_equal(got, want)
+
+
+def test_random_sharded_programs():
+    """Random coupling graphs, 1-3 sharded qubits, classic and fused exchanges, with and without restoring the sharding:
+    emulated result == oracle, structural invariants of every local program hold."""
+    from tests.plan_check import check_plan
+
+    rng = np.random.default_rng(777)
+    for _ in range(10):
+        g = int(rng.integers(1, 4))
+        n = min(int(rng.integers(13 + g, 16 + g)), 16)
+        order, reps = int(rng.choice([1, 2])), int(rng.choice([1, 2]))
+        dens = float(rng.choice([0.3, 0.6, 1.0]))
+        peer, rest = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        A = rng.uniform(0.05, 1.0, (n, n)) * (rng.random((n, n)) < dens)
+        K = (A + A.T) / 2.0
+        np.fill_diagonal(K, 0.0)
+        w = rng.uniform(0.5, 4.0, n)
+        Kc, wc = oc.canonicalise(n, K, w)
+        prog = plan_describe(Kc, wc, 0.1, order, reps, n_local=n - g, peer_exchange=peer, restore_sharding=rest)
+        z, p = oc.term_list(Kc, wc)
+        psi0 = oc.initial_state(wc)
+        ref = oc.evolve_product_formula(psi0.copy(), z, p, 0.1, reps, order)
+        got, perm, _, _ = simulate_sharded(prog, n, n - g, psi0, wc)
+        inv = [0] * n
+        for q in range(n):
+            inv[perm[q]] = q
+        assert 1.0 - oc.fidelity(permute_bits(got, n, inv), ref) < 1e-12
+        for op in prog["ops"]:
+            if op["kind"] == "local":
+                check_plan(op["plan"])
