@@ -82,6 +82,7 @@ struct xyk_handle_s {
     };
     std::map<std::string, ShardCacheEntry> shard_cache;  // compiled sharded programs by (problem, formula, sharding on entry)
     int64_t shard_compiles = 0;
+    int shard_gates = 0, shard_rounds = 0, shard_passes = 0;  // totals of the sharded call in flight (stats at its end)
     size_t shard_pos = 0;
     bool exchange_pending = false;
     std::vector<int> ex_out, ex_in;
@@ -693,6 +694,12 @@ int run_shard_steps(xyk_handle h) {
         XYK_CUDA(h, cudaStreamSynchronize(h->stream));  // the host's collective runs on another stream
         return XYK_NEED_EXCHANGE;
     }
+    if (h->shard_passes > 0) {  // the per-program bookkeeping of run_program_tiled saw only the last local program
+        h->stats.last_gates = h->shard_gates;
+        h->stats.last_rounds = h->shard_rounds;
+        h->stats.last_passes = h->shard_passes;
+        h->shard_gates = h->shard_rounds = h->shard_passes = 0;
+    }
     h->shard_steps.clear();
     h->shard_pos = 0;
     h->shard_phase = 0;
@@ -721,9 +728,9 @@ int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1, do
     if (hit != h->shard_cache.end()) {
         h->shard_steps = hit->second.steps;
         h->shard_pos = 0;
-        h->stats.last_gates = hit->second.gates;
-        h->stats.last_rounds = hit->second.rounds;
-        h->stats.last_passes = hit->second.passes;
+        h->stats.last_gates = h->shard_gates = hit->second.gates;
+        h->stats.last_rounds = h->shard_rounds = hit->second.rounds;
+        h->stats.last_passes = h->shard_passes = hit->second.passes;
         h->stats.last_layers1 = l1;
         return XYK_OK;
     }
@@ -776,9 +783,9 @@ int build_shard_steps(xyk_handle h, const std::vector<Segment>& segs, int l1, do
         h->shard_steps.push_back(std::move(st));
     }
     h->perm = saved_perm;
-    h->stats.last_gates = gates;
-    h->stats.last_rounds = rounds;
-    h->stats.last_passes = passes;
+    h->stats.last_gates = h->shard_gates = gates;
+    h->stats.last_rounds = h->shard_rounds = rounds;
+    h->stats.last_passes = h->shard_passes = passes;
     h->stats.last_layers1 = l1;
     if (h->shard_cache.size() > 64) h->shard_cache.clear();
     xyk_handle_s::ShardCacheEntry& ce = h->shard_cache[key];
