@@ -5,6 +5,10 @@
 // F & 2: sign flips (LOP3 on the high word) of 32 of the 64 values after the load and before the store
 // F & 4: gates behind a runtime mask test each, coefficients from the kernel parameter (constant bank)
 // F & 8: runtime strides: eight per-thread bases + eight warp-uniform offsets recomputed every round
+// F & 16 (with F & 1): planar tile (Re plane, Im plane) and a WARP-uniform half: no sign flips, every lane of a warp
+//         touches the same component; the half-1 warps run the gates with negated (uniform) coefficients
+// F & 32 (with F & 1, without F & 4): program order of a round = loads of the first gate's 32 operands, first gate,
+//         the other 32 loads, gates 2..G-1, stores of the 32 values the last gate does not touch, last gate, other stores
 // Prints cycles per round of three tiles (the three co-resident CTAs together); floors: shared pipe 3 x 1024, FP64 3 x G x 48 x 2.13.
 // nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/overlap_probe.cu -o overlap_probe
 #include <cstdio>
@@ -34,9 +38,45 @@ __global__ void __launch_bounds__(128, 3) rounds(int iters, const __grid_constan
     const uint32_t smask = (tid & 1u) << 31;
     // lane-linear windows: thread t owns 16-byte column t of 32 rows of 2 KiB (conflict free for both widths)
     const uint32_t w128 = base + tid * 16u;
-    const uint32_t w64 = base + (tid >> 1) * 16u + (tid & 1u) * 8u;
+    // interleaved: lane pair (2k, 2k+1) shares a 16-byte slot; planar: warps 0,1 work on the Re plane, warps 2,3 on the Im plane
+    const uint32_t w64 = (F & 16) ? base + (tid >> 6) * 32768u + (tid & 63u) * 8u : base + (tid >> 1) * 16u + (tid & 1u) * 8u;
+    const uint32_t row64 = (F & 16) ? 512u : 1024u;  // byte stride of register index j
     __syncthreads();
     const long long t0 = clock64();
+    if constexpr ((F & 32) != 0) {
+        // explicit program order: the first gate starts on its 32 operands while the other 32 loads are in flight, the
+        // values the last gate does not touch are stored before it runs
+        const double ca = 1e-9, cb = -1e-9;
+        auto gate = [&](int x, int y) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int j0 = insert_zero(insert_zero(m, x), y);
+                const int jA = j0 | (1 << x), jB = j0 | (1 << y);
+                double &p = (__builtin_popcount(jA >> 3) & 1) ? v[jB] : v[jA], &q = (__builtin_popcount(jA >> 3) & 1) ? v[jA] : v[jB];
+                p = fma(ca, q, p); q = fma(cb, p, q); p = fma(ca, q, p);
+            }
+        };
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int s = 1; s < G - 1; ++s) gate(s / 3, 3 + s % 3);
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                if (((j >> 2) & 1) == ((j >> 5) & 1)) sts64(w64 + j * 1024, v[j]);   // untouched by the last gate (2, 5)
+            gate(2, 5);
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                if (((j >> 2) & 1) != ((j >> 5) & 1)) sts64(w64 + j * 1024, v[j]);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                if ((j & 1) != ((j >> 3) & 1)) v[j] = lds64(w64 + (j ^ (it & 1) ^ ((it & 1) << 3)) * 1024);  // operands of the first gate (0, 3)
+            gate(0, 3);
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+                if ((j & 1) == ((j >> 3) & 1)) v[j] = lds64(w64 + (j ^ (it & 1) ^ ((it & 1) << 3)) * 1024);
+            __syncthreads();
+        }
+    } else
     for (int it = 0; it < iters; ++it) {
         // gates
         if (F & 4) {
@@ -46,7 +86,8 @@ __global__ void __launch_bounds__(128, 3) rounds(int iters, const __grid_constan
                 for (int y = 3; y < 6; ++y) {
                     const int slot = 3 * x + (y - 3);
                     if (slot < G && (D.mask & (1u << slot))) {
-                        const double ca = D.ca[slot], cb = D.cb[slot];
+                        const bool neg = (F & 16) && (tid >> 6);  // warp-uniform: the half-1 warps rotate by the opposite angle
+                        const double ca = neg ? -D.ca[slot] : D.ca[slot], cb = neg ? -D.cb[slot] : D.cb[slot];
 #pragma unroll
                         for (int m = 0; m < 16; ++m) {
                             const int j0 = insert_zero(insert_zero(m, x), y);
@@ -81,14 +122,14 @@ __global__ void __launch_bounds__(128, 3) rounds(int iters, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
                 double x = v[j];
-                if ((F & 2) && (__builtin_popcount(j >> 3) & 1)) x = flip(x, smask);
-                sts64((F & 8) ? bh[j >> 3] + lo[j & 7] : w64 + j * 1024, x);
+                if ((F & 2) && !(F & 16) && (__builtin_popcount(j >> 3) & 1)) x = flip(x, smask);
+                sts64((F & 8) ? bh[j >> 3] + lo[j & 7] : w64 + j * row64, x);
             }
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
-                v[j] = lds64((F & 8) ? bh[(j >> 3) ^ (it & 1)] + lo[j & 7] : w64 + (j ^ (it & 1)) * 1024);
-                if ((F & 2) && (__builtin_popcount(j >> 3) & 1)) v[j] = flip(v[j], smask);
+                v[j] = lds64((F & 8) ? bh[(j >> 3) ^ (it & 1)] + lo[j & 7] : w64 + (j ^ (it & 1)) * row64);
+                if ((F & 2) && !(F & 16) && (__builtin_popcount(j >> 3) & 1)) v[j] = flip(v[j], smask);
             }
         } else {
 #pragma unroll
@@ -134,5 +175,7 @@ int main() {
     run<9, 0>(cyc, sink); run<9, 1>(cyc, sink); run<9, 3>(cyc, sink); run<9, 4>(cyc, sink); run<9, 5>(cyc, sink); run<9, 7>(cyc, sink); run<9, 15>(cyc, sink);
     run<0, 0>(cyc, sink); run<0, 1>(cyc, sink); run<0, 15>(cyc, sink);
     run<5, 0>(cyc, sink); run<5, 15>(cyc, sink);
+    run<9, 7>(cyc, sink); run<9, 23>(cyc, sink);   // interleaved + sign flips vs planar + warp-uniform half (static strides)
+    run<9, 1>(cyc, sink); run<9, 33>(cyc, sink);   // default program order vs loads / stores interleaved with the first / last gate
     return 0;
 }
