@@ -554,6 +554,7 @@ bool use_tiled(xyk_handle h) {
     if (h->dtype != 0) return false;  // complex64 runs gate by gate in this build
     if (h->engine_opt == XYK_ENGINE_SIMPLE) return false;
     if (h->nlocal < kTB) return false;
+    if (h->nlocal > 31) return false;  // the fused store of the pass kernel indexes amplitudes with 32-bit offsets (2 * 2^31 would wrap)
     if (h->engine_opt == XYK_ENGINE_TILED) return true;
     return h->nlocal >= 13;
 }
@@ -963,8 +964,8 @@ int xyk_apply_layers(xyk_handle h, double delta, int order, int reps) {
     XYK_CHECK(h, std::isfinite(delta), XYK_ERR_INVALID, "delta must be finite");
     XYK_CUDA(h, cudaSetDevice(h->device));
     if (h->world > 1) {
-        XYK_CHECK(h, h->dtype == 0 && h->nlocal >= kTB, XYK_ERR_UNSUPPORTED,
-                  "sharded evolution needs complex128 and at least 12 local qubits");
+        XYK_CHECK(h, h->dtype == 0 && h->nlocal >= kTB && h->nlocal <= 31, XYK_ERR_UNSUPPORTED,
+                  "sharded evolution needs complex128 and 12 to 31 local qubits");
         XYK_CHECK(h, !h->exchange_pending && h->shard_steps.empty(), XYK_ERR_STATE, "a sharded call is still in flight");
         int l1s = 0;
         std::vector<Segment> ssegs = build_sequence(h->pairs, delta, order, reps, &l1s);
