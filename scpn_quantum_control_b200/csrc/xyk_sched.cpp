@@ -799,6 +799,16 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             r.reverse = g[rp.gate_idx[r.cidx[0]]].reverse;
             std::sort(r.cidx.begin(), r.cidx.end());
         };
+        // upper bound of what a register set can run: the undone gates it contains (prunes most closures once the
+        // pool holds K good candidates; a pruned set could not have entered the pool, so the result is unchanged)
+        std::vector<uint64_t> undone;
+        for (size_t c = 0; c < rp.gate_idx.size(); ++c)
+            if (!cd[c]) undone.push_back((1ull << g[rp.gate_idx[c]].i) | (1ull << g[rp.gate_idx[c]].j));
+        auto contained = [&](uint64_t set) {
+            int cnt = 0;
+            for (uint64_t m : undone) cnt += (m & set) == m;
+            return cnt;
+        };
         {
             const int nr = std::min(RB, tn);
             std::vector<int> idx(nr);
@@ -806,7 +816,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             while (true) {
                 uint64_t rm = 0;
                 for (int k = 0; k < nr; ++k) rm |= 1ull << tq[idx[k]];
-                round_closure(g, rp.gate_idx, cd, rm, ex);
+                if (2 * contained(rm) > pool.floor_score()) round_closure(g, rp.gate_idx, cd, rm, ex);
+                else ex.clear();
                 if (2 * (int)ex.size() > pool.floor_score()) {
                     RawRound r;
                     r.rmask = rm;
@@ -828,8 +839,9 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         while (true) {
             uint64_t sm = 0;
             for (int k = 0; k < RS; ++k) sm |= 1ull << tq[idx[k]];
+            const int bound = 2 * std::min(contained(sm), (RS / 2) * (RS - RS / 2)) - 1;
             for (int H : {RS / 2, Hunb}) {
-                if (H <= 0) continue;
+                if (H <= 0 || bound <= pool.floor_score()) continue;
                 std::vector<int> sub(H);
                 for (int k = 0; k < H; ++k) sub[k] = k;
                 while (true) {
