@@ -403,10 +403,16 @@ std::shared_ptr<Program> get_program(xyk_handle h, double delta, int order, int 
 // the twelve instantiations of the pass kernel: shear-form rotations or not, peer (fused exchange) stores or not,
 // and which unbalanced split round is compiled in: none (the lean kernel, ~30 % smaller), 2 | 4, or 1 | 5
 using PassKernel = void (*)(const double2*, double2*, const Desc, uint64_t, const PeerPtrs);
+// kPassGroups = 3: one CTA per SM with three tile groups in a token ring; 1: three free-running CTAs per SM
+#ifndef XYK_PASS_GROUPS
+#define XYK_PASS_GROUPS 3
+#endif
+constexpr int kPassGroups = XYK_PASS_GROUPS;
+constexpr int kPassMinBlocks = kPassGroups == 1 ? 3 : 1;
 template <int UNB>
 PassKernel pass_kernel_unb(bool lift, bool peer) {
-    if (lift) return peer ? tile_pass_kernel<kTB, kRB, true, 3, true, UNB> : tile_pass_kernel<kTB, kRB, true, 3, false, UNB>;
-    return peer ? tile_pass_kernel<kTB, kRB, false, 3, true, UNB> : tile_pass_kernel<kTB, kRB, false, 3, false, UNB>;
+    if (lift) return peer ? tile_pass_kernel<kTB, kRB, true, kPassMinBlocks, true, UNB, kPassGroups> : tile_pass_kernel<kTB, kRB, true, kPassMinBlocks, false, UNB, kPassGroups>;
+    return peer ? tile_pass_kernel<kTB, kRB, false, kPassMinBlocks, true, UNB, kPassGroups> : tile_pass_kernel<kTB, kRB, false, kPassMinBlocks, false, UNB, kPassGroups>;
 }
 PassKernel pass_kernel_fn(bool lift, bool peer, int unb) {
     return unb == 2 ? pass_kernel_unb<2>(lift, peer) : (unb == 1 ? pass_kernel_unb<1>(lift, peer) : pass_kernel_unb<0>(lift, peer));
@@ -421,11 +427,15 @@ int desc_unbalanced(const Desc& d) {
 }
 
 int configure_pass_kernels(xyk_handle h) {
-    const int smem = (int)tile_bytes<kTB>();
+    const int smem = kPassGroups * (int)tile_bytes<kTB>();
     for (int k = 0; k < 12; ++k) XYK_CUDA(h, cudaFuncSetAttribute(pass_kernel_fn(k & 1, k & 2, k >> 2), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
-    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel_fn(true, false, 0), 1 << (kTB - kRB), smem));
+    XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel_fn(true, false, 0), kPassGroups << (kTB - kRB), smem));
     if (occ < 1) occ = 1;
+#ifdef XYK_TRACE
+    if (const char* e = std::getenv("XYK_PASS_OCC")) occ = std::max(1, std::min(occ, std::atoi(e)));  // development build only
+    std::fprintf(stderr, "pass kernel occupancy: %d CTAs per SM\n", occ);
+#endif
     h->pass_grid = occ * h->sm_count;
     return XYK_OK;
 }
@@ -443,14 +453,20 @@ int begin_program(xyk_handle h, Program& prog) {
     return relayout(h, target);
 }
 
+#ifdef XYK_TRACE
+unsigned long long* g_trace_ptr = nullptr;
+long g_trace_pass = -1;
+size_t g_trace_words = 0;
+#endif
+
 // passes [p0, p1) of a program.  peer = true: the (single) pass scatters into the mapped buffers of
 // every rank (the exchange fused into the store); the caller has fenced the ranks around it.
 int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
     const Plan& plan = prog.plan;
     const uint64_t ntiles = 1ull << (h->nlocal - kTB);
-    const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)h->pass_grid);
-    const int smem = (int)tile_bytes<kTB>();
-    const int nthr = 1 << (kTB - kRB);
+    const int grid = (int)std::min<uint64_t>((ntiles + kPassGroups - 1) / kPassGroups, (uint64_t)h->pass_grid);
+    const int smem = kPassGroups * (int)tile_bytes<kTB>();
+    const int nthr = kPassGroups << (kTB - kRB);
     PeerPtrs peers{};
     if (peer)
         for (int r = 0; r < h->world; ++r) peers.p[r] = (double2*)h->peer_buf[r][h->cur ^ 1];
@@ -474,6 +490,12 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
             }
             cudaEventRecord(h->pass_events[2 * p], h->stream);
         }
+#ifdef XYK_TRACE
+        {   // development build only: the phase timeline of ONE pass (index g_trace_pass of the program) is recorded
+            unsigned long long* tp = ((long)p == g_trace_pass) ? g_trace_ptr : nullptr;
+            cudaMemcpyToSymbolAsync(xyk_trace_buf, &tp, sizeof(tp), 0, cudaMemcpyHostToDevice, h->stream);
+        }
+#endif
         static const int ablate = std::getenv("XYK_ABLATE") ? std::atoi(std::getenv("XYK_ABLATE")) : 0;  // timing experiments only (wrong results)
         if (ablate) {
             auto d = prog.descs[p];
@@ -1327,7 +1349,7 @@ int64_t xyk_plan_describe(int n_local, int dtype, const double* K, const double*
         cfg.TB = kTB;
         cfg.RB = kRB;
         cfg.max_rounds = kMaxRounds;
-        apply_env(cfg);
+            apply_env(cfg);
         std::string js;
         if (n_local < n) {  // sharded program: the g highest logical qubits start on the rank bits
             std::vector<int> glob;
@@ -1354,3 +1376,23 @@ int xyk_batch_run(int device, int n, int B, const double* K, const double* omega
 }
 
 }  // extern "C"
+
+#ifdef XYK_TRACE
+// development build only (tools/trace_pass.py): record the per-warp phase timeline of pass `pass_index`
+extern "C" int xyk_debug_trace_begin(int pass_index, int k0, int nk) {
+    g_trace_words = (size_t)148 * 3 * 4 * kTraceMaxE;
+    if (!g_trace_ptr && cudaMalloc(&g_trace_ptr, g_trace_words * 8) != cudaSuccess) return XYK_ERR_CUDA;
+    cudaMemset(g_trace_ptr, 0, g_trace_words * 8);
+    cudaMemcpyToSymbol(xyk_trace_k0, &k0, sizeof(int));
+    cudaMemcpyToSymbol(xyk_trace_nk, &nk, sizeof(int));
+    g_trace_pass = pass_index;
+    return cudaDeviceSynchronize() == cudaSuccess ? XYK_OK : XYK_ERR_CUDA;
+}
+extern "C" int64_t xyk_debug_trace_read(unsigned long long* dst, int64_t max_words) {
+    if (!g_trace_ptr) return -1;
+    cudaDeviceSynchronize();
+    const size_t nw = std::min<size_t>((size_t)max_words, g_trace_words);
+    if (cudaMemcpy(dst, g_trace_ptr, nw * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)nw;
+}
+#endif

@@ -95,6 +95,7 @@ struct SchedConfig {
     int RB = 5;            // register bits (amplitudes per thread = 2^RB)
     int need_shared = 3;   // consecutive tiles must share this many qubits (contiguous output chunks)
     int max_rounds = 14;   // rounds a single pass descriptor can carry
+    int max_pass_gates = 1 << 20;  // gates a single pass may carry (no limit in the current kernel)
     int lane_bits = 3;     // lowest physical bits that must map to lanes for fused global I/O (2^3 x 16 B = 128 B)
     bool fuse_io = true;   // plan first / last rounds so that they can touch global memory directly
     bool split_rounds = true;  // allow split rounds (RB + 1 register qubits over two real half-states)

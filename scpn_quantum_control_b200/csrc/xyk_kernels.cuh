@@ -36,7 +36,7 @@ template <> struct cplx<float> { using type = float2; };
 // 128-byte bank window (conflict free).  Cost: 14 % more shared memory than a dense tile.
 __host__ __device__ constexpr uint32_t pad_slot(uint32_t x) { return x + (x >> 3) + (x >> 6) + (x >> 9); }
 template <int TB>
-constexpr uint32_t tile_bytes() {
+__host__ __device__ constexpr uint32_t tile_bytes() {
     return (pad_slot((1u << TB) - 1u) + 1u) * 16u;
 }
 
@@ -666,11 +666,53 @@ __device__ __forceinline__ void split_global_store(const double (&v)[NV], double
     }
 }
 
-template <int TB, int RB, bool LIFT, int MINB, bool PEER, int UNB>
-__global__ void __launch_bounds__(1 << (TB - RB), MINB)
+// ---- development only (-DXYK_TRACE, tools/trace build): per-warp phase timeline of the pass kernel ----
+#ifdef XYK_TRACE
+__device__ unsigned long long* xyk_trace_buf = nullptr;   // [warp slot][kTraceMaxE]
+__device__ int xyk_trace_k0 = 100, xyk_trace_nk = 4;     // traced window: the k0-th .. (k0+nk-1)-th tile of every CTA
+constexpr int kTraceMaxE = 256;
+__device__ __forceinline__ unsigned long long trace_clock() {
+    unsigned long long c;
+    asm volatile("mov.u64 %0, %%clock64;\n" : "=l"(c)::"memory");
+    return c;
+}
+// consume `x` (a shared-memory store of its high word) so that the following clock read issues after x is available
+__device__ __forceinline__ void trace_consume(uint32_t scratch, double x) {
+    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(scratch), "r"(__double2hiint(x)) : "memory");
+}
+#define XYK_TR(code)                                                                  \
+    do {                                                                              \
+        if (tr_on && tr_i < kTraceMaxE) tr_p[tr_i++] = (trace_clock() << 8) | (unsigned long long)(code); \
+    } while (0)
+#define XYK_TR_DEP(code, x)                      \
+    do {                                         \
+        if (tr_on) {                             \
+            trace_consume(tr_scratch, (x));      \
+            XYK_TR(code);                        \
+        }                                        \
+    } while (0)
+#else
+#define XYK_TR(code) do { } while (0)
+#define XYK_TR_DEP(code, x) do { } while (0)
+#endif
+
+// NG = 1: one tile per CTA (MINB CTAs per SM run free).  NG = 3: one CTA per SM holds three tile groups of 2^(TB-RB) threads,
+// each with its own tile buffer; the shared-memory phases of the groups (round-0 load | store, barrier, load | global store) take
+// turns through a token handed round the ring 0 -> 1 -> 2 (named barriers): while one group moves data the other two do
+// arithmetic, which free-running CTAs do not keep up (measured: their FP64 and shared-memory phases drift into phase).
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int TB, int RB, bool LIFT, int MINB, bool PEER, int UNB, int NG>
+__global__ void __launch_bounds__(NG << (TB - RB), MINB)
 tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                  const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles, const __grid_constant__ PeerPtrs peers) {
     constexpr int NT = TB - RB, NTHR = 1 << NT, NREG = 1 << RB, NSLOT = RB * (RB - 1) / 2;
+    static_assert(NG == 1 || NG == 3, "one free-running tile per CTA, or three tile groups in a token ring");
     constexpr int RS = RB + 1, NV = 1 << RS, HS = RS / 2;  // split rounds: register qubits, reals per thread, group size
     static_assert(RB == 5, "round header packs six register-bit offsets; split rounds need an even RB + 1");
     static_assert(HS * HS <= NSLOT, "split-round slots share the coefficient table");
@@ -679,12 +721,28 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     // per round: {rs0|rs1<<16, rs2|rs3<<16, rs4|rs5<<16, mask|sync<<16|nleft<<17 (nleft = 0: complex round)}, {ts0|ts1<<16, ts2|ts3<<16, ts4|ts5<<16, ts6}
     // rs = byte stride of a register bit, ts = byte stride of a thread bit
     __shared__ __align__(16) uint4 hdr_tab[2 * (kMaxRounds + 1)];
-    __shared__ __align__(8) unsigned long long tile_mbar;
-    const uint32_t mbar_u32 = smem_addr_once(&tile_mbar);
-    const uint32_t tile_u32 = smem_addr_once(smem_raw);
+    __shared__ __align__(8) unsigned long long tile_mbar[NG];
+    const uint32_t tid_cta = tid_once();
+    // tile group of this thread; the lane-0 broadcast tells the compiler that it is warp-uniform (uniform registers for the
+    // tile index and everything derived from it)
+    const uint32_t grp = NG == 1 ? 0u : __shfl_sync(0xffffffffu, tid_cta >> NT, 0);
+    const uint32_t mbar_u32 = smem_addr_once(&tile_mbar[grp]);
+    const uint32_t tile_u32 = smem_addr_once(smem_raw + (size_t)grp * tile_bytes<TB>());
     const uint32_t hdr_u32 = smem_addr_once(hdr_tab);
-    double2* tile = reinterpret_cast<double2*>(smem_raw);
-    const uint32_t tid = tid_once();
+    double2* tile = reinterpret_cast<double2*>(smem_raw + (size_t)grp * tile_bytes<TB>());
+    const uint32_t tid = NG == 1 ? tid_cta : (tid_cta & (uint32_t)(NTHR - 1));  // thread index inside the group
+    // barrier over the threads of one tile group; token ring: barrier 4 + g is "the token arrives at group g"
+    auto group_sync = [&]() {
+        if constexpr (NG == 1) __syncthreads();
+        else named_bar_sync(1u + grp, NTHR);
+    };
+    // two tokens: kind 0 = the store phase of a round (shared-memory stores or the global store), kind 1 = the load phase
+    auto token_acquire = [&](uint32_t kind) {
+        if constexpr (NG > 1) named_bar_sync(4u + 3u * kind + grp, 2 * NTHR);
+    };
+    auto token_release = [&](uint32_t kind) {
+        if constexpr (NG > 1) named_bar_arrive(4u + 3u * kind + (grp + 1u == (uint32_t)NG ? 0u : grp + 1u), 2 * NTHR);
+    };
     const uint32_t flags = P.flags;
     const int nr = P.nrounds;
     const uint32_t half = tid & 1u;   // split rounds: which real half-state this thread holds
@@ -766,33 +824,61 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     // split rounds: the odd half sees every rotation with the opposite angle; equivalently it keeps the
     // Im-role elements (f = 1) negated and uses the same coefficients (which must stay warp-uniform)
     const uint32_t smask = half << 31;
+#ifdef XYK_TRACE
+    __shared__ uint32_t tr_scratch_mem[4];
+    const uint32_t tr_scratch = smem_addr_once(&tr_scratch_mem[tid >> 5]);
+    unsigned long long* tr_p = xyk_trace_buf ? xyk_trace_buf + (((size_t)blockIdx.x * NG + grp) * (NTHR / 32) + (tid >> 5)) * kTraceMaxE : nullptr;
+    int tr_i = 2, tr_k = 0;
+    bool tr_on = false;
+    const unsigned long long tr_c0 = trace_clock();
+    if (tr_p && (tid & 31u) == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr_p[0] = smid;
+    }
+#endif
     if (tid == 0) mbar_init(mbar_u32, 1);
-    __syncthreads();  // tables and mbarrier visible
+    __syncthreads();  // tables and mbarriers visible
+    if (NG > 1 && grp + 1u == (uint32_t)NG) {  // both tokens start at group 0
+        token_release(0);
+        token_release(1);
+    }
 
     // Fused load = the whole 64 KiB tile arrives by bulk asynchronous copies (eight 8 KiB segments) into the front of the
     // tile buffer; it is issued as soon as the previous tile's last round has read its data out of the
     // buffer, so the global load overlaps that round's arithmetic and the global store.
     uint32_t tile_parity = 0;
-    if ((flags & kPassFuseLoad) && tid == 0) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)blockIdx.x << TB), mbar_u32);
+    // tile indices fit 32 bits (at most 2^31 local amplitudes)
+    const uint32_t tstride = gridDim.x * NG;   // tiles between two consecutive tiles of a group
+    const uint32_t tfirst = blockIdx.x * NG + grp;
+    const uint32_t ntile32 = (uint32_t)ntiles;
+    if ((flags & kPassFuseLoad) && tid == 0 && tfirst < ntile32) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)tfirst << TB), mbar_u32);
 
-    if (flags & kPassStagger) {
-        // co-resident CTAs (block ids i, i + #SM, i + 2 #SM) start pad0 ns apart (spin on the ns timer)
-        const uint32_t k = blockIdx.x / ((gridDim.x + 2) / 3);
-        if (k) {
-            uint64_t t0, t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            do {
-                __nanosleep(200);
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            } while (t1 - t0 < (uint64_t)k * (uint64_t)P.pad0);
+    // every group of a CTA runs the same number of iterations: the token ring needs all of them (a group without a tile left
+    // only passes the token on)
+    for (uint32_t t = tfirst; t - grp < ntile32; t += tstride) {  // as long as group 0 of this CTA has a tile
+        if (NG > 1 && t >= ntile32) {
+            for (int k = 0; k < nr; ++k) {
+                token_acquire(1);
+                token_release(1);
+                token_acquire(0);
+                token_release(0);
+            }
+            continue;
         }
-    }
-    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const double2* src = in + (t << TB);
+        const double2* src = in + ((uint64_t)t << TB);
+#ifdef XYK_TRACE
+        // traced window: the first nk tiles this CTA starts after k0 * 1024 cycles of kernel time (co-resident CTAs overlap in time)
+        if (tr_p != nullptr && (tid & 31u) == 0) {
+            if (tr_k == 0 && (long long)(trace_clock() - tr_c0) > (long long)xyk_trace_k0 * 1024) tr_k = 1;
+            tr_on = tr_k >= 1 && tr_k <= xyk_trace_nk;
+            if (tr_k >= 1) ++tr_k;
+        }
+#endif
         auto prefetch_next = [&]() {
-            if (tid == 0 && !(flags & kPassNoPrefetch) && t + gridDim.x < ntiles) {
-                if (flags & kPassPfEvictLast) prefetch_l2_bulk_evict_last(in + ((t + gridDim.x) << TB), (uint32_t)(sizeof(double2) << TB));
-                else prefetch_l2_bulk(in + ((t + gridDim.x) << TB), (uint32_t)(sizeof(double2) << TB));
+            if (tid == 0 && !(flags & kPassNoPrefetch) && t + tstride < ntile32) {
+                if (flags & kPassPfEvictLast) prefetch_l2_bulk_evict_last(in + ((uint64_t)(t + tstride) << TB), (uint32_t)(sizeof(double2) << TB));
+                else prefetch_l2_bulk(in + ((uint64_t)(t + tstride) << TB), (uint32_t)(sizeof(double2) << TB));
             }
         };
         if (!(flags & (kPassPfLate | kPassFuseLoad))) prefetch_next();
@@ -814,18 +900,27 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             const bool split = nl != 0u;
             // unbalanced split round (UNB = 2: 2 | 4, UNB = 1: 1 | 5): separate code, present only in the kernel instantiation for it
             const bool unb = UNB != 0 && nl == (uint32_t)UNB;
+            const Round& R = P.rounds[r];  // gate coefficients stay in the constant bank: a uniform operand of DFMA (measured: a
+                                           // shared-memory coefficient stream into vector registers costs 4-5 % of the layer)
             const uint32_t boff1 = boff + 8u - (half << 4);  // split rounds: base of the elements with f(j) = 1
             if ((flags & kPassPfLate) && !(flags & kPassFuseLoad) && r == nr - 1) prefetch_next();
-            const Round& R = P.rounds[r];  // gate coefficients stay in the constant bank: a uniform operand of DFMA
-                                           // (measured: DFMA with three vector-register sources issues ~15 % slower)
             // complex round: v[2j], v[2j+1] = Re, Im of register index j (RB bits);
             // split round:   v[j] = one real component of register index j (RB + 1 bits)
             double v[NV];
 
             // ---------------- load ----------------
+#ifdef XYK_TRACE
+            if (r > 0 && tr_on) {  // the barrier before this round has released once a shared-memory load returns
+                trace_consume(tr_scratch, lds64(hdr_u32));
+                XYK_TR(3);
+            }
+#endif
             if (r == 0 && (flags & kPassFuseLoad)) {
+                XYK_TR(1);
                 mbar_wait(mbar_u32, tile_parity);
                 tile_parity ^= 1u;
+                token_acquire(1);
+                XYK_TR(2);
                 if (unb) {
                     if constexpr (UNB) {
                         uint32_t st[RS];
@@ -874,14 +969,15 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 }
             } else {
                 if (r == 0) {
-                    __syncthreads();  // every warp is done reading the previous tile out of shared memory
+                    token_acquire(1);
+                    group_sync();  // every warp is done reading the previous tile out of shared memory
 #pragma unroll
                     for (int k = 0; k < NREG; ++k) {
                         const uint32_t hi = pad_slot((uint32_t)k << NT);  // constant after unrolling
                         cp_async16(&tile[ld_slot + hi], src + ((uint32_t)k << NT) + tid);
                     }
                     cp_async_wait_all();
-                    __syncthreads();
+                    group_sync();
                 }
                 // address = per-thread base of the high register bits (8 vector adds per burst) + warp-uniform
                 // offset of the low register bits: LDS [R + UR], no per-access vector arithmetic
@@ -929,10 +1025,12 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 }
             }
 
+            token_release(1);  // loads issued: the next group may start its load phase
+            XYK_TR_DEP(4, v[NV - 1]);
             // the last round holds the tile in registers: the buffer is free for the next tile
             if ((flags & kPassFuseLoad) && (flags & kPassFuseStore) && r == nr - 1) {
-                __syncthreads();
-                if (tid == 0 && t + gridDim.x < ntiles) bulk_load_tile<TB>(tile_u32, in + ((t + gridDim.x) << TB), mbar_u32);
+                group_sync();
+                if (tid == 0 && t + tstride < ntile32) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)(t + tstride) << TB), mbar_u32);
             }
 
             // ---------------- diagonal phase (complex round 0 only) ----------------
@@ -961,24 +1059,30 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     split_gates<(UNB ? UNB : 2), RS, NV, LIFT>(v, mask, R);
                 }
             } else if (split) {
+                // a full round (all nine gates: the common case) runs as straight-line code: no mask test between the gates, so
+                // the next gate's first rotations issue while the previous gate's last ones are still in the FP64 pipe
+                auto split_round = [&](auto all) {
 #pragma unroll
-                for (int x = 0; x < HS; ++x) {
+                    for (int x = 0; x < HS; ++x) {
 #pragma unroll
-                    for (int y = HS; y < RS; ++y) {
-                        const int slot = HS * x + (y - HS);
-                        if (mask & (1u << slot)) {
-                            const double ca = R.ca[slot], cb = R.cb[slot];
+                        for (int y = HS; y < RS; ++y) {
+                            const int slot = HS * x + (y - HS);
+                            if (decltype(all)::value || (mask & (1u << slot))) {
+                                const double ca = R.ca[slot], cb = R.cb[slot];
 #pragma unroll
-                            for (int m = 0; m < NV / 4; ++m) {
-                                const int j0 = insert_zero(insert_zero(m, x), y);
-                                const int jA = j0 | (1 << x), jB = j0 | (1 << y);
-                                // half 0 holds Re(A), Im(B) when f(jA) = 0 and Im(A), Re(B) otherwise (roles swap)
-                                if (__builtin_popcount(jA >> HS) & 1) rotate2<LIFT>(v[jB], v[jA], ca, cb);
-                                else rotate2<LIFT>(v[jA], v[jB], ca, cb);
+                                for (int m = 0; m < NV / 4; ++m) {
+                                    const int j0 = insert_zero(insert_zero(m, x), y);
+                                    const int jA = j0 | (1 << x), jB = j0 | (1 << y);
+                                    // half 0 holds Re(A), Im(B) when f(jA) = 0 and Im(A), Re(B) otherwise (roles swap)
+                                    if (__builtin_popcount(jA >> HS) & 1) rotate2<LIFT>(v[jB], v[jA], ca, cb);
+                                    else rotate2<LIFT>(v[jA], v[jB], ca, cb);
+                                }
                             }
                         }
                     }
-                }
+                };
+                if (mask == (1u << (HS * HS)) - 1u) split_round(std::true_type{});
+                else split_round(std::false_type{});
             } else {
 #pragma unroll
                 for (int x = 0; x < RB; ++x) {
@@ -1000,6 +1104,20 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             }
 
             // ---------------- store / exchange ----------------
+#ifdef XYK_TRACE
+            if (tr_on) {  // every value the gates may have touched last is available
+                trace_consume(tr_scratch, v[NV - 1]);
+                trace_consume(tr_scratch, v[NV - 2]);
+                trace_consume(tr_scratch, v[NV / 2 - 1]);
+                trace_consume(tr_scratch, v[NV / 2 + 1]);
+                trace_consume(tr_scratch, v[NV / 4]);
+                trace_consume(tr_scratch, v[NV / 4 + 3]);
+                trace_consume(tr_scratch, v[5]);
+                trace_consume(tr_scratch, v[2]);
+                XYK_TR(5);
+            }
+#endif
+            token_acquire(0);
             if (r == nr - 1 && (flags & kPassFuseStore)) {
                 const uint64_t dbase = obase + st_d;
                 if constexpr (PEER) {
@@ -1074,12 +1192,14 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                         for (int j = 0; j < NREG; ++j) __stcs(bq[j >> 2] + lo[j & 3], make_double2(v[2 * j], v[2 * j + 1]));
                     }
                 }
+                token_release(0);
+                XYK_TR(6);
             } else {
                 // next round's header and base slot: issued ahead of the stores, back before the barrier
                 const uint4 hdr_next = lds_u4(hdr_u32 + (uint32_t)(r + 1) * 32u);
                 const uint4 thr_next = lds_u4(hdr_u32 + (uint32_t)(r + 1) * 32u + 16u);
                 // tile boundary: the previous tile's last round (other warps) must be done reading
-                if (r == 0 && (flags & kPassFuseLoad)) __syncthreads();
+                if (r == 0 && (flags & kPassFuseLoad)) group_sync();
                 if (unb) {
                     if constexpr (UNB) {
                         split_exchange<(UNB ? UNB : 2), RS, NV, true>(v, boff, half, rb, smask);
@@ -1117,8 +1237,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
                     for (int j = 0; j < NREG; ++j) sts128(bh[j >> 2] + lo[j & 3], make_double2(v[2 * j], v[2 * j + 1]));
                 }
-                if ((hdr.w >> 16) & 1u) __syncthreads();
+                XYK_TR(6);
+                if (r + 1 < nr) token_release(0);
+                if ((hdr.w >> 16) & 1u) group_sync();
                 else __syncwarp();
+                if (r + 1 < nr) token_acquire(1);
                 hdr = hdr_next;
                 boff = tile_u32 + thread_base(thr_next, ((hdr_next.w >> 17) & 3u) != 0u);
             }
@@ -1139,11 +1262,16 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     }
                 store_out<PEER>(out, peers, P.nq, dbase + dk, tile[st_l + pad_slot(lk)]);
             }
+            token_release(0);
             if (flags & kPassFuseLoad) {
-                __syncthreads();
-                if (tid == 0 && t + gridDim.x < ntiles) bulk_load_tile<TB>(tile_u32, in + ((t + gridDim.x) << TB), mbar_u32);
+                group_sync();
+                if (tid == 0 && t + tstride < ntile32) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)(t + tstride) << TB), mbar_u32);
             }
         }
+    }
+    if (NG > 1 && grp == 0) {  // absorb the last hand-overs (barrier state balanced at exit)
+        token_acquire(0);
+        token_acquire(1);
     }
 }
 

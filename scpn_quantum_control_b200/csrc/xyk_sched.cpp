@@ -1381,7 +1381,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     {
         std::vector<PlanPass> out;
         for (auto& pp : plan.passes) {
-            if ((int)pp.rounds.size() <= cfg.max_rounds) {
+            if ((int)pp.rounds.size() <= cfg.max_rounds && pp.ngates <= cfg.max_pass_gates) {
                 out.push_back(std::move(pp));
                 continue;
             }
@@ -1389,7 +1389,11 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
             size_t off = 0;
             const size_t total = pp.rounds.size();
             while (off < total) {
-                const size_t cnt = std::min((size_t)cfg.max_rounds, total - off);
+                size_t cnt = 0;  // rounds of this piece: at most max_rounds, at most max_pass_gates gates (the kernel's coefficient list)
+                for (int g = 0; cnt < std::min((size_t)cfg.max_rounds, total - off); ++cnt) {
+                    g += pp.rounds[off + cnt].ngates;
+                    if (g > cfg.max_pass_gates && cnt > 0) break;
+                }
                 PlanPass piece = pp;
                 piece.rounds.assign(pp.rounds.begin() + off, pp.rounds.begin() + off + cnt);
                 // the piece's store reads the whole tile out of shared memory: block-wide barrier after its last
