@@ -35,6 +35,13 @@ struct Program {
     std::vector<int> loc2log;       // logical qubit of plan index l (identity on a single GPU)
     std::vector<Desc> descs;        // one per pass
     std::vector<char> lift;         // shear form allowed for the pass
+    std::vector<void*> dev_tabs;    // device tables owned by the program (fused-phase factors)
+    Program() = default;
+    Program(const Program&) = delete;
+    Program& operator=(const Program&) = delete;
+    ~Program() {
+        for (void* p : dev_tabs) cudaFree(p);
+    }
 };
 
 struct ShardStep {
@@ -258,8 +265,9 @@ int relayout(xyk_handle h, const std::vector<int>& target) {
     return XYK_OK;
 }
 
-void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, const PlanPass& pp,
+void fill_desc(xyk_handle h, Program& prog, const std::vector<int>& loc2log, const PlanPass& pp,
                const std::vector<int>& perm_in, Desc& d, bool& lift_ok) {
+    const Plan& plan = prog.plan;
     std::memset(&d, 0, sizeof(d));
     d.nq = plan.nq;
     d.nrounds = (int)pp.rounds.size();
@@ -290,24 +298,48 @@ void fill_desc(xyk_handle h, const Plan& plan, const std::vector<int>& loc2log, 
     // fused diagonal phase: weights per INPUT physical bit, register table of round 0
     if (pp.has_phase && h->fuse_phase && !h->zterms.empty()) {
         d.flags |= kPassHasPhase;
-        d.ph_tau = pp.ztau;
-        std::vector<double> wlog(h->n, 0.0);
+        std::vector<double> wlog(h->n, 0.0), ph_w(kMaxQ, 0.0);  // ph_w: omega of the logical qubit on INPUT physical bit b
         for (const auto& z : h->zterms) wlog[z.i] = z.w;
         std::vector<char> is_local(h->n, 0);
         for (int l = 0; l < plan.nq; ++l) {
-            d.ph_w[perm_in[l]] = wlog[loc2log[l]];
+            ph_w[perm_in[l]] = wlog[loc2log[l]];
             is_local[loc2log[l]] = 1;
         }
         // sharded qubits: their bit is fixed by the rank (the caller guarantees h->perm is current for them)
         double pc = 0.0;
         for (int q = 0; q < h->n; ++q)
             if (!is_local[q]) pc += wlog[q] * (((h->rank >> (h->perm[q] - h->nlocal)) & 1) ? -1.0 : 1.0);
-        d.ph_const = pc;
-        const PlanRound& r0 = pp.rounds.front();
+        const PlanRound& r0 = pp.rounds.front();   // a complex round (the schedule compiler puts the phase on one)
         for (int j = 0; j < (1 << kRB); ++j) {
             double ph = 0.0;
-            for (int k = 0; k < kRB; ++k) ph += d.ph_w[r0.regpos[k]] * (((j >> k) & 1) ? -1.0 : 1.0);
+            for (int k = 0; k < kRB; ++k) ph += ph_w[r0.regpos[k]] * (((j >> k) & 1) ? -1.0 : 1.0);
             d.ph_reg[j] = make_double2(std::cos(pp.ztau * ph), std::sin(pp.ztau * ph));
+        }
+        // table factors of the thread bits (+ the constant rank part) and of the tile-id bits in two chunks
+        const int nhi = plan.nq - kTB;
+        d.ph_b1 = std::min(nhi, kPhTabBits);
+        std::vector<double2> tab(kPhTabSize, make_double2(1.0, 0.0));
+        for (int v = 0; v < (1 << (kTB - kRB)); ++v) {
+            double ph = pc;
+            for (int b = 0; b < kTB - kRB; ++b) ph += ph_w[r0.thrpos[b]] * (((v >> b) & 1) ? -1.0 : 1.0);
+            tab[v] = make_double2(std::cos(pp.ztau * ph), std::sin(pp.ztau * ph));
+        }
+        for (int c = 0; c < 2; ++c) {
+            const int lo = c == 0 ? 0 : d.ph_b1, hi = c == 0 ? d.ph_b1 : nhi;
+            for (int v = 0; v < (1 << (hi - lo)); ++v) {
+                double ph = 0.0;
+                for (int b = lo; b < hi; ++b) ph += ph_w[kTB + b] * (((v >> (b - lo)) & 1) ? -1.0 : 1.0);
+                tab[(c == 0 ? kPhTabLo : kPhTabHi) + v] = make_double2(std::cos(pp.ztau * ph), std::sin(pp.ztau * ph));
+            }
+        }
+        void* dtab = nullptr;
+        if (nhi - d.ph_b1 > kPhTabBits || cudaMalloc(&dtab, tab.size() * sizeof(double2)) != cudaSuccess ||
+            cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess) {
+            if (dtab) cudaFree(dtab);
+            d.flags &= ~kPassHasPhase;  // falls back to the separate phase sweep (run_passes)
+        } else {
+            prog.dev_tabs.push_back(dtab);
+            d.ph_tab = (const double2*)dtab;
         }
     }
     const std::vector<PlanRound>& rounds_used = pp.rounds;
@@ -370,7 +402,7 @@ void finish_program(xyk_handle h, Program& prog) {
     std::vector<int> perm(prog.plan.start_perm);
     for (size_t p = 0; p < prog.plan.passes.size(); ++p) {
         bool lift = true;
-        fill_desc(h, prog.plan, prog.loc2log, prog.plan.passes[p], perm, prog.descs[p], lift);
+        fill_desc(h, prog, prog.loc2log, prog.plan.passes[p], perm, prog.descs[p], lift);
         prog.lift[p] = lift ? 1 : 0;
         std::vector<int> np(perm);
         for (int q = 0; q < prog.plan.nq; ++q) np[q] = prog.plan.passes[p].out_of_in[perm[q]];

@@ -376,6 +376,7 @@ __global__ void convert_kernel(const typename cplx<from>::type* __restrict__ src
 // fused tile pass
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxRounds = 14;
+constexpr int kPhTabLo = 128, kPhTabBits = 10, kPhTabHi = kPhTabLo + (1 << kPhTabBits), kPhTabSize = kPhTabHi + (1 << kPhTabBits);
 
 constexpr uint32_t kPassFuseLoad = 1u;   // round 0 reads its amplitudes straight from global memory
 constexpr uint32_t kPassFuseStore = 2u;  // the last round writes its amplitudes straight to global memory
@@ -413,10 +414,15 @@ struct PassDesc {
     uint32_t st_reg_idx[8];  // fused store: output INDEX stride (1 << output bit) of the LAST round's register bit k
     uint32_t arr_reg[8];     // fused load: byte stride of round 0's register bit k in the arrival layout (arrival_stride_bytes)
     uint64_t out_base;       // peer passes: output-index contribution of this device's rank bits
-    double ph_const;         // fused phase: contribution of the sharded (rank) bits, constant on this device
-    double ph_tau;           // fused phase: exp(+i tau sum_b w_b (1 - 2 bit_b)) over all input bits
-    double ph_w[kMaxQ];      // omega of the logical qubit on INPUT physical bit b
-    double2 ph_reg[1 << RB]; // phase factor of register index j in round 0
+    // fused phase exp(+i tau sum_b w_b (1 - 2 bit_b)) over all input bits = product of four table factors (built on the host):
+    //   ph_tab[thread id]                      round 0's thread qubits and the sharded (rank) bits
+    //   ph_tab[kPhTabLo + (tile & mask)]       the low ph_b1 tile-id bits
+    //   ph_tab[kPhTabHi + (tile >> ph_b1)]     the other tile-id bits
+    //   ph_reg[register index]                 round 0's register qubits
+    const double2* ph_tab;
+    int32_t ph_b1;
+    int32_t pad1;
+    double2 ph_reg[1 << RB];
     Round rounds[kMaxRounds];
 };
 
@@ -812,15 +818,6 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             }
         st_l = pad_slot(st_l);
     }
-    // fused phase: contribution of this thread's round-0 index bits (round 0 of a phase pass is a complex round)
-    double ph_thr = P.ph_const;
-    if (flags & kPassHasPhase) {
-#pragma unroll
-        for (int b = 0; b < NT; ++b) {
-            const double wv = P.ph_w[P.rounds[0].thrpos[b]];
-            ph_thr += ((tid >> b) & 1u) ? -wv : wv;
-        }
-    }
     // split rounds: the odd half sees every rotation with the opposite angle; equivalently it keeps the
     // Im-role elements (f = 1) negated and uses the same coefficients (which must stay warp-uniform)
     const uint32_t smask = half << 31;
@@ -1035,13 +1032,12 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 
             // ---------------- diagonal phase (complex round 0 only) ----------------
             if (r == 0 && (flags & kPassHasPhase)) {
-                double ph = ph_thr;
-                for (int b = 0; b < P.nq - TB; ++b) {
-                    const double wv = P.ph_w[TB + b];
-                    ph += ((t >> b) & 1ull) ? -wv : wv;
-                }
-                double sn, cs;
-                sincos(P.ph_tau * ph, &sn, &cs);
+                // tile / thread part of the phase: three table factors (no sincos, no loop over the tile-id bits)
+                const double2 f0 = __ldg(P.ph_tab + tid);
+                const double2 f1 = __ldg(P.ph_tab + kPhTabLo + (t & ((1u << P.ph_b1) - 1u)));
+                const double2 f2 = __ldg(P.ph_tab + kPhTabHi + (t >> P.ph_b1));
+                const double gr = f1.x * f2.x - f1.y * f2.y, gi = f1.x * f2.y + f1.y * f2.x;
+                const double cs = f0.x * gr - f0.y * gi, sn = f0.x * gi + f0.y * gr;
 #pragma unroll
                 for (int j = 0; j < NREG; ++j) {
                     const double2 f = P.ph_reg[j];
