@@ -149,23 +149,56 @@ bool perm_is_identity(xyk_handle h) {
     return true;
 }
 
+// |psi0> = prod_q Ry(omega_q mod 2 pi)|0> in the current layout: three chunk tables built on the host
 template <typename real>
 int launch_init(xyk_handle h) {
-    QubitTable T{};
-    T.nq = h->n;
-    T.nlocal = h->nlocal;
-    T.rank = h->rank;
     const double two_pi = 2.0 * M_PI;
+    std::vector<double> cq(h->n), sq(h->n);
     for (int q = 0; q < h->n; ++q) {
         double a = std::fmod(h->omega[q], two_pi);  // Python's % : result has the sign of the modulus
         if (a < 0.0) a += two_pi;
-        T.c[q] = std::cos(a / 2.0);
-        T.s[q] = std::sin(a / 2.0);
-        T.pos[q] = (uint8_t)h->perm[q];
+        cq[q] = std::cos(a / 2.0);
+        sq[q] = std::sin(a / 2.0);
     }
+    std::vector<int> log_of_bit(h->n, -1);  // logical qubit on physical bit b
+    for (int q = 0; q < h->n; ++q) log_of_bit[h->perm[q]] = q;
+    const int nl = h->nlocal;
     using C = typename cplx<real>::type;
-    const uint64_t dim = 1ull << h->nlocal;
-    init_product_kernel<real><<<grid_for(h, dim, 256), 256, 0, h->stream>>>((C*)h->buf[h->cur], T);
+    if (nl < 4) {  // a handful of amplitudes: written from the host
+        std::vector<C> psi0((size_t)1 << nl);
+        for (size_t p = 0; p < psi0.size(); ++p) {
+            double x = 1.0;
+            for (int b = 0; b < h->n; ++b) {
+                const int bit = b < nl ? (int)((p >> b) & 1) : ((h->rank >> (b - nl)) & 1);
+                x *= bit ? sq[log_of_bit[b]] : cq[log_of_bit[b]];
+            }
+            psi0[p].x = (real)x;
+            psi0[p].y = (real)0;
+        }
+        XYK_CUDA(h, cudaMemcpyAsync(h->buf[h->cur], psi0.data(), psi0.size() * sizeof(C), cudaMemcpyHostToDevice, h->stream));
+        XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+        return XYK_OK;
+    }
+    int b1 = std::min(nl, 11), b2 = std::min(nl, 22);
+    if (nl - b2 > 11) {
+        b1 = (nl + 2) / 3;
+        b2 = b1 + (nl - b1 + 1) / 2;
+    }
+    XYK_CHECK(h, b1 <= 11 && b2 - b1 <= 11 && nl - b2 <= 11, XYK_ERR_UNSUPPORTED, "product-state tables support at most 33 local qubits");
+    double rank_factor = 1.0;
+    for (int b = nl; b < h->n; ++b) rank_factor *= ((h->rank >> (b - nl)) & 1) ? sq[log_of_bit[b]] : cq[log_of_bit[b]];
+    double* htab = reinterpret_cast<double*>(h->h_out);   // pinned staging: 3 x kTabStride doubles
+    const int lo[3] = {0, b1, b2}, hi[3] = {b1, b2, nl};
+    for (int c = 0; c < 3; ++c)
+        for (int v = 0; v < (1 << (hi[c] - lo[c])); ++v) {
+            double x = c == 2 ? rank_factor : 1.0;
+            for (int b = lo[c]; b < hi[c]; ++b) x *= ((v >> (b - lo[c])) & 1) ? sq[log_of_bit[b]] : cq[log_of_bit[b]];
+            htab[c * kTabStride + v] = x;
+        }
+    XYK_CUDA(h, cudaMemcpyAsync(h->d_tab, htab, sizeof(double) * 3 * kTabStride, cudaMemcpyHostToDevice, h->stream));
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));  // the staging buffer is reused by other calls
+    init_product_kernel<real><<<grid_for(h, 1ull << nl, 256), 256, 0, h->stream>>>((C*)h->buf[h->cur], reinterpret_cast<const double*>(h->d_tab),
+                                                                              kTabStride, nl, b1, b2);
     h->stats.kernel_launches++;
     XYK_CUDA(h, cudaGetLastError());
     return XYK_OK;
@@ -619,10 +652,114 @@ void launch_obs_multi(xyk_handle h, const ObsSpec& S, int grid) {
     xy_expect_multi_kernel<real, M><<<grid, 256, 0, h->stream>>>((const C*)h->buf[h->cur], S, (double2*)h->d_partial);
 }
 
+// Rounds of one observable sweep: the tile-local positions in `want` (with their rows) are spread over register rounds of five;
+// the three lowest thread bits of a round take one position of each pair {0,9}, {1,10}, {2,11} (conflict-free reads of the
+// arrival layout), so a round never holds both positions of a pair in registers.
+bool plan_obs_rounds(std::vector<std::pair<int, int>> want /* (tile-local position, row) */, ObsTileSpec& S) {
+    S.nrounds = 0;
+    auto has = [](const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+    auto partner = [](int p) { return p < 3 ? p + 9 : (p >= 9 ? p - 9 : -1); };
+    while (!want.empty()) {
+        if (S.nrounds == 3) return false;
+        ObsTileSpec::Round& R = S.rounds[S.nrounds++];
+        std::vector<int> regs, rows;
+        for (auto it = want.begin(); it != want.end() && (int)regs.size() < 4;) {
+            if (partner(it->first) >= 0 && has(regs, partner(it->first))) { ++it; continue; }
+            regs.push_back(it->first);
+            rows.push_back(it->second);
+            it = want.erase(it);
+        }
+        for (int p = 3; (int)regs.size() < 4 && p < 9; ++p)   // fill with positions that are not measured here
+            if (!has(regs, p)) {
+                regs.push_back(p);
+                rows.push_back(-1);
+            }
+        if ((int)regs.size() < 4) return false;
+        std::vector<int> thr;
+        for (int c = 0; c < 3; ++c) thr.push_back(!has(regs, c) ? c : c + 9);
+        for (int p = 0; p < 12; ++p)
+            if (!has(regs, p) && !has(thr, p)) thr.push_back(p);
+        if (thr.size() != 8) return false;
+        for (int k = 0; k < 4; ++k) {
+            R.regpos[k] = (uint8_t)regs[k];
+            R.row[k] = (int16_t)rows[k];
+        }
+        for (int b = 0; b < 8; ++b) R.thrpos[b] = (uint8_t)thr[b];
+    }
+    return true;
+}
+
+// <X_q>, <Y_q> for local qubits -> d_out[2q], d_out[2q+1]: twelve physical bits per sweep through shared-memory tiles
+// (complex128, n_local >= 13): the contiguous low twelve bits first, then 12 - nb further bits per sweep next to a chunk of 2^nb
+// contiguous amplitudes.  n_local = 30: three sweeps (the per-qubit loop of the reference reads the state thirty times).
+int xy_expect_tiled_device(xyk_handle h) {
+    const int nl = h->nlocal;
+    std::vector<int> row_of_bit(nl, -1);
+    for (int q = 0; q < h->n; ++q) {
+        if (h->perm[q] < nl) row_of_bit[h->perm[q]] = q;
+        else cudaMemsetAsync((double2*)h->d_partial + (size_t)q * kRedBlocks, 0, sizeof(double2) * kRedBlocks, h->stream);
+    }
+    const uint64_t ntiles = 1ull << (nl - 12);
+    const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)3 * h->sm_count);
+    const int smem = (int)arrival_bytes<12>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        XYK_CUDA(h, cudaFuncSetAttribute(xy_expect_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int rem = nl - 12;
+    // chunk size of the strided sweeps: 2^nb amplitudes.  256-byte chunks (nb = 4, eight new bits per sweep) unless larger
+    // chunks need no more sweeps; 128-byte chunks (nine bits per sweep) run slower than one more sweep (512 copies per tile)
+    int nb = 4;
+    if (const char* e = std::getenv("XYK_OBS_NB")) nb = std::atoi(e);
+    else
+        for (int c = 8; c > 4; --c)
+            if ((rem + (12 - c) - 1) / (12 - c) <= (rem + 7) / 8) { nb = c; break; }
+    const int per = 12 - nb, nsweeps = 1 + (rem + per - 1) / per;
+    int next_hi = 12;
+    for (int sw = 0; sw < nsweeps; ++sw) {
+        ObsTileSpec S{};
+        S.nlocal = nl;
+        S.stride = kRedBlocks;
+        std::vector<std::pair<int, int>> want;
+        if (sw == 0) {
+            S.nb = 5;
+            for (int p = 0; p < 12; ++p) {
+                S.tile_pos[p] = (uint8_t)p;
+                want.push_back({p, row_of_bit[p]});
+            }
+        } else {
+            S.nb = nb;
+            const int left = nl - next_hi, sweeps_left = nsweeps - sw;
+            const int take = std::min(per, (left + sweeps_left - 1) / sweeps_left);   // even split over the remaining sweeps
+            for (int p = 0; p < nb; ++p) S.tile_pos[p] = (uint8_t)p;
+            std::vector<int> hi;
+            for (int k = 0; k < take; ++k) hi.push_back(next_hi + k);
+            for (int b = nb; (int)hi.size() < per; ++b)   // pad the tile with bits that are not measured in this sweep
+                if (b < next_hi || b >= next_hi + take) hi.push_back(b);
+            std::sort(hi.begin(), hi.end());
+            for (int k = 0; k < per; ++k) {
+                S.tile_pos[nb + k] = (uint8_t)hi[k];
+                if (hi[k] >= next_hi && hi[k] < next_hi + take) want.push_back({nb + k, row_of_bit[hi[k]]});
+            }
+            next_hi += take;
+        }
+        XYK_CHECK(h, plan_obs_rounds(want, S), XYK_ERR_STATE, "observable sweep: no conflict-free round assignment");
+        xy_expect_tile_kernel<<<grid, 128, smem, h->stream>>>((const double2*)h->buf[h->cur], S, (double2*)h->d_partial);
+        h->stats.kernel_launches++;
+        h->stats.state_sweeps++;
+    }
+    xy_finalize_kernel<<<h->n, 128, 0, h->stream>>>((const double2*)h->d_partial, grid, kRedBlocks, h->d_out);
+    h->stats.kernel_launches++;
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
 // <X_q>, <Y_q> for local qubits -> d_out[2q], d_out[2q+1] (already multiplied by 2).
 // Five qubits per sweep (each thread holds the 32 amplitudes they span): ceil(n_local / 5) reads of the
 // state instead of the n reads of the per-qubit loop (reference: pauli.rs:195-211 does n passes).
 int xy_expect_device(xyk_handle h) {
+    if (h->dtype == 0 && h->tiled_obs && h->nlocal >= 13) return xy_expect_tiled_device(h);
     const int grid_cap = kRedBlocks;
     std::vector<std::pair<int, int>> loc;  // (physical position, logical qubit)
     for (int q = 0; q < h->n; ++q) {
@@ -918,7 +1055,7 @@ int xyk_create(int n_qubits, int dtype, int device, int world_size, int rank, xy
     ok = ok && cudaMalloc(&h->d_tab, sizeof(double2) * 3 * kTabStride) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_partial, sizeof(double) * kPartialDoubles) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_out, sizeof(double) * 4096) == cudaSuccess;
-    ok = ok && cudaMallocHost(&h->h_out, sizeof(double) * 4096) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->h_out, sizeof(double) * 8192) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
     if (!ok) {
         std::string msg = std::string("scratch allocation failed: ") + cudaGetErrorString(cudaGetLastError());

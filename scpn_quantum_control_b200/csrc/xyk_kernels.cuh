@@ -84,28 +84,22 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* smem /* >= NV
 // ---------------------------------------------------------------------------------------------
 // gate-by-gate kernels
 // ---------------------------------------------------------------------------------------------
-struct QubitTable {
-    double c[kMaxQ];      // cos(theta_q / 2)
-    double s[kMaxQ];      // sin(theta_q / 2)
-    uint8_t pos[kMaxQ];   // physical bit of logical qubit q; >= nlocal means the bit comes from `rank`
-    int32_t nq;           // total logical qubits
-    int32_t nlocal;       // local physical bits
-    int32_t rank;         // value of the physical bits >= nlocal
-};
-
 // psi0[k] = prod_q (bit_q ? sin : cos)(theta_q/2)     (xy_kuramoto.py:236-242)
+// The product over the local physical bits comes from three host-built chunk tables (bits [0,b1), [b1,b2), [b2,nlocal));
+// the factor of the sharded (rank) bits is folded into the last table.
 template <typename real>
-__global__ void init_product_kernel(typename cplx<real>::type* __restrict__ psi, const __grid_constant__ QubitTable T) {
-    const uint64_t dim = 1ull << T.nlocal;
-    const uint64_t hi = (uint64_t)T.rank << T.nlocal;
+__global__ void init_product_kernel(typename cplx<real>::type* __restrict__ psi, const double* __restrict__ tab, int stride, int nlocal,
+                                    int b1, int b2) {
+    using C = typename cplx<real>::type;
+    const uint64_t dim = 1ull << nlocal;
+    const uint32_t m0 = (1u << b1) - 1u, m1 = (1u << (b2 - b1)) - 1u;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < dim; p += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t full = p | hi;
-        double v = 1.0;
-        for (int q = 0; q < T.nq; ++q) v *= ((full >> T.pos[q]) & 1ull) ? T.s[q] : T.c[q];
-        typename cplx<real>::type o;
+        const double v = __ldg(&tab[(uint32_t)p & m0]) * __ldg(&tab[stride + ((uint32_t)(p >> b1) & m1)]) *
+                         __ldg(&tab[2 * stride + (uint32_t)(p >> b2)]);
+        C o;
         o.x = (real)v;
         o.y = (real)0;
-        psi[p] = o;
+        __stcs(psi + p, o);
     }
 }
 
@@ -701,6 +695,119 @@ __device__ __forceinline__ void trace_consume(uint32_t scratch, double x) {
 #define XYK_TR(code) do { } while (0)
 #define XYK_TR_DEP(code, x) do { } while (0)
 #endif
+
+// ---------------------------------------------------------------------------------------------
+// <X_q>, <Y_q> of up to twelve qubits per sweep (complex128): tiles of 2^12 amplitudes -- a contiguous chunk of 2^nb amplitudes
+// times 12 - nb further physical bits -- arrive in shared memory by bulk asynchronous copies (arrival layout); per tile up to
+// three register rounds read 32 amplitudes per thread and accumulate conj(psi_k) psi_{k|m} for their register bits in FP64.
+// Reference semantics: scpn_quantum_engine/src/pauli.rs:195-211 (one sweep PER QUBIT there).
+// ---------------------------------------------------------------------------------------------
+struct ObsTileSpec {
+    int32_t nlocal, nb, nrounds, stride;
+    uint8_t tile_pos[12];        // physical bit of tile-local position p (the first nb are 0 .. nb-1)
+    struct Round {
+        uint8_t regpos[4];       // tile-local position of register bit k
+        uint8_t thrpos[8];       // tile-local position of thread bit b (the three lowest: one of each pair {0,9}, {1,10}, {2,11});
+                                 // thrpos[7]: the bit the two batches of a round differ in
+        int16_t row[4];          // row of `partial` register bit k reports to, -1: not measured in this round
+    } rounds[3];
+};
+
+__global__ void __launch_bounds__(128, 3)
+xy_expect_tile_kernel(const double2* __restrict__ psi, const __grid_constant__ ObsTileSpec S, double2* __restrict__ partial) {
+    constexpr int TB = 12, RB = 4, NREG = 1 << RB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar_mem;
+    __shared__ double red[2 * 32];
+    const uint32_t tile_u32 = smem_addr_once(smem_raw), mbar = smem_addr_once(&mbar_mem);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t ntiles = 1u << (S.nlocal - TB);
+    const int nhi = TB - S.nb;                       // strided tile bits
+    const uint32_t chunk_bytes = 16u << S.nb;
+    double acc[3][2 * RB];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 2 * RB; ++k) acc[r][k] = 0.0;
+    uint32_t tbase[3];   // per round: byte offset of this thread's base amplitude in the arrival layout
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        tbase[r] = 0;
+#pragma unroll
+        for (int b = 0; b < 7; ++b)
+            if ((tid >> b) & 1u) tbase[r] += arrival_stride_bytes(S.rounds[r].thrpos[b]);
+    }
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    auto issue = [&](uint32_t t) {
+        uint64_t base = (uint64_t)t << S.nb;
+        for (int i = 0; i < nhi; ++i) base = insert_zero64(base, S.tile_pos[S.nb + i]);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(16u << TB) : "memory");
+        for (uint32_t ch = tid; ch < (1u << nhi); ch += 128u) {   // chunk index = tile-local index >> nb
+            uint64_t off = 0;
+            for (int i = 0; i < nhi; ++i)
+                if ((ch >> i) & 1u) off |= 1ull << S.tile_pos[S.nb + i];
+            const uint32_t x = ch << S.nb;                      // tile-local index of the chunk's first amplitude
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                             tile_u32 + (x + (x >> 9)) * 16u),
+                         "l"(psi + base + off), "r"(chunk_bytes), "r"(mbar)
+                         : "memory");
+        }
+    };
+    uint32_t parity = 0;
+    if (blockIdx.x < ntiles) issue(blockIdx.x);
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r < S.nrounds) {
+                const uint32_t s0 = arrival_stride_bytes(S.rounds[r].regpos[0]), s1 = arrival_stride_bytes(S.rounds[r].regpos[1]);
+                const uint32_t s2 = arrival_stride_bytes(S.rounds[r].regpos[2]), s3 = arrival_stride_bytes(S.rounds[r].regpos[3]);
+                const uint32_t sb = arrival_stride_bytes(S.rounds[r].thrpos[7]);
+#pragma unroll
+                for (int batch = 0; batch < 2; ++batch) {
+                    double ar[NREG], ai[NREG];
+                    const uint32_t b0 = tile_u32 + tbase[r] + (batch ? sb : 0u);
+                    const uint32_t bh[4] = {b0, b0 + s2, b0 + s3, b0 + s2 + s3};
+                    const uint32_t lo[4] = {0u, s0, s1, s0 + s1};
+#pragma unroll
+                    for (int j = 0; j < NREG; ++j) {
+                        const double2 v = lds128(bh[j >> 2] + lo[j & 3]);
+                        ar[j] = v.x;
+                        ai[j] = v.y;
+                    }
+                    if (r == S.nrounds - 1 && batch == 1) {  // the buffer is free: the next tile's copies overlap the arithmetic
+                        __syncthreads();
+                        if (t + gridDim.x < ntiles) issue(t + gridDim.x);
+                    }
+#pragma unroll
+                    for (int k = 0; k < RB; ++k) {
+#pragma unroll
+                        for (int j = 0; j < NREG; ++j) {
+                            if (!((j >> k) & 1)) {
+                                const int f = j | (1 << k);
+                                acc[r][2 * k] += ar[j] * ar[f] + ai[j] * ai[f];
+                                acc[r][2 * k + 1] += ar[j] * ai[f] - ai[j] * ar[f];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // block reduction, one row per measured qubit
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            double v[2] = {acc[r][2 * k], acc[r][2 * k + 1]};
+            block_sum<2>(v, red);
+            const int row = r < S.nrounds ? S.rounds[r].row[k] : -1;
+            if (tid == 0 && row >= 0) partial[(size_t)row * S.stride + blockIdx.x] = make_double2(v[0], v[1]);
+        }
+}
 
 // NG = 1: one tile per CTA (MINB CTAs per SM run free).  NG = 3: one CTA per SM holds three tile groups of 2^(TB-RB) threads,
 // each with its own tile buffer; the shared-memory phases of the groups (round-0 load | store, barrier, load | global store) take

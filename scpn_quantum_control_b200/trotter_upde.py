@@ -46,14 +46,8 @@ class QuantumUPDESolver:
     def set_coupling(self, K) -> None:
         """Re-parameterise K on the live state without re-allocating (realtime feedback ticks,
         reference: control/realtime_feedback.py:98-137)."""
-        K = np.asarray(K, dtype=np.float64)
-        self._solver._validate_coupling_inputs(self.n_layers, K, self.omega)
-        self.K = K.copy()
-        self._solver.K = K.copy()
-        np.fill_diagonal(self._solver.K, 0.0)
-        self._solver._exact_reps_cache.clear()
-        if self._solver._engine is not None:
-            self._solver._engine.set_problem(self._solver.K, self.omega)
+        self._solver.update_problem(K)
+        self.K = self._solver.K.copy()
 
     def statevector(self) -> np.ndarray:
         return self._solver.statevector()

@@ -185,6 +185,19 @@ class QuantumKuramotoSolver:
             self._engine = eng
         return self._engine
 
+    def update_problem(self, K_coupling, omega_natural=None) -> None:
+        """Re-parameterise (K, omega) on the live engine: same validation as the constructor, the
+        device statevector and its buffers stay as they are (the realtime-feedback controller of the
+        reference re-scales K every tick on a live state, control/realtime_feedback.py:98-137)."""
+        K = _as_real_numeric_array("K_coupling", K_coupling)
+        omega = self.omega if omega_natural is None else _as_real_numeric_array("omega_natural", omega_natural)
+        self._validate_coupling_inputs(self.n, K, omega)
+        np.fill_diagonal(K, 0.0)
+        self.K, self.omega = K, omega
+        self._exact_reps_cache.clear()
+        if self._engine is not None:
+            self._engine.set_problem(self.K, self.omega)
+
     def close(self) -> None:
         if self._engine is not None:
             self._engine.close()
