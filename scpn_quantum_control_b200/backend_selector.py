@@ -23,7 +23,9 @@ import numpy as np
 from .engine import device_count, device_memory
 from .xy_kuramoto import QuantumKuramotoSolver
 
-GPU_STATEVECTOR_MAX_QUBITS_1GPU = 32  # 2 x 64 GiB ping-pong buffers fit one 180 GB B200
+# local qubits per GPU the fused tile-pass engine takes (32-bit amplitude offsets inside a shard; 2 x 32 GiB ping-pong
+# buffers of the 180 GB).  n_local = 32 would still fit the memory but runs gate by gate, so it is not recommended.
+GPU_STATEVECTOR_MAX_QUBITS_1GPU = 31
 
 
 def has_gpu() -> bool:

@@ -86,6 +86,42 @@ class TrotterEvolutionConfig:
             )
 
 
+_CALIBRATE_DIRECT_MAX_N = 26   # halving check on the full problem up to here (1 GiB state; an S6 repetition costs < 1 s)
+_CALIBRATE_PROXY_N = 18        # size of the reduced problem used above that
+
+
+def halving_reps(observe, tol_step: float, max_reps: int = 256) -> int:
+    """A-posteriori choice of the repetition count: ``observe(reps)`` returns the observables after one
+    interval run with ``reps`` repetitions; double ``reps`` until two consecutive results agree to
+    ``tol_step`` and return the coarser of the two (a 6th-order formula: error(reps/2) ~ 64 error(reps))."""
+    reps, prev = 1, None
+    while reps <= max_reps:
+        cur = np.asarray(observe(reps))
+        if prev is not None and np.max(np.abs(cur - prev)) <= tol_step:
+            return max(1, reps // 2)
+        prev = cur
+        reps *= 2
+    return max_reps
+
+
+def reduced_problem_for_calibration(K: np.ndarray, omega: np.ndarray, n_sub: int) -> tuple[np.ndarray, np.ndarray]:
+    """The ``n_sub`` qubits with the largest local energy scale sum_j |K_ij| + |omega_i|, their coupling
+    block scaled up so that its largest row sum equals the full problem's (the splitting error is driven
+    by the local energy scale times the step)."""
+    K = np.asarray(K, dtype=np.float64)
+    omega = np.asarray(omega, dtype=np.float64)
+    n = K.shape[0]
+    if n_sub >= n:
+        return K.copy(), omega.copy()
+    row = np.abs(K).sum(axis=1)
+    idx = np.sort(np.argsort(-(row + np.abs(omega)), kind="stable")[:n_sub])
+    Ks = K[np.ix_(idx, idx)].copy()
+    sub_row = np.abs(Ks).sum(axis=1).max()
+    if sub_row > 0.0:
+        Ks *= max(1.0, row.max() / sub_row)
+    return Ks, omega[idx].copy()
+
+
 class QuantumKuramotoSolver:
     """Exact-statevector simulation of Kuramoto oscillators on one B200 (or a sharded group)."""
 
@@ -126,8 +162,12 @@ class QuantumKuramotoSolver:
         # distributed=True: the state is sharded over the ranks of the default torch.distributed
         # (NCCL) process group, one process per GPU; every rank calls the same methods
         self.distributed = bool(distributed)
+        if self.distributed and dtype != "complex128":
+            raise ValueError("distributed=True supports dtype='complex128' only (sharded states are complex128)")
         self._engine = None
         self._exact_reps_cache: dict[tuple[float, float], int] = {}
+        self._calibrate_direct_max_n = _CALIBRATE_DIRECT_MAX_N
+        self.exact_calibration: dict | None = None
 
     # -- validation (same messages as the reference) ---------------------------------------------
     @staticmethod
@@ -219,7 +259,11 @@ class QuantumKuramotoSolver:
     def _calibrated_exact_reps(self, step_dt: float, nsteps: int = 1) -> int:
         """Smallest power-of-two repetition count of the 6th-order composition whose observables
         over one interval agree with the doubled count to ``exact_tol / nsteps`` (a-posteriori
-        check; the error of a unitary splitting accumulates at most linearly in the step count)."""
+        halving check; the error of a unitary splitting accumulates at most linearly in the step
+        count).  Up to ``_CALIBRATE_DIRECT_MAX_N`` qubits the check runs on a private engine of the
+        full problem; above that (and for sharded states) on a reduced problem of the most strongly
+        coupled qubits with the couplings scaled up to the full problem's largest row sum, and the
+        count it finds is doubled.  ``self.exact_calibration`` records which of the two was used."""
         tol_step = self.exact_tol / max(4, int(nsteps))
         key = (round(float(step_dt), 15), tol_step)
         for (k_dt, k_tol), v in self._exact_reps_cache.items():
@@ -227,32 +271,29 @@ class QuantumKuramotoSolver:
                 return v
         if step_dt == 0.0:
             return 1
-        eng = XYKEngine(self.n, dtype=self.dtype, device=self.device) if self.n <= 20 and not self.distributed else None
-        if eng is None:  # calibration at large n costs too much memory: use a norm-based rule
-            scale = float(np.abs(self.K).sum() / 2.0 + np.abs(self.omega).sum())
-            reps = max(1, int(np.ceil(step_dt * scale / 6.0)))
-            self._exact_reps_cache[key] = reps
-            return reps
+        direct = self.n <= self._calibrate_direct_max_n and not self.distributed
+        if direct:
+            n_cal, K_cal, w_cal, safety = self.n, self.K, self.omega, 1
+            self.exact_calibration = {"kind": "direct", "n": self.n}
+        else:
+            n_cal = min(self.n, _CALIBRATE_PROXY_N)
+            K_cal, w_cal = reduced_problem_for_calibration(self.K, self.omega, n_cal)
+            safety = 2
+            self.exact_calibration = {"kind": "reduced_problem", "n": n_cal, "safety_factor": safety}
+        eng = XYKEngine(n_cal, dtype=self.dtype, device=self.device)
         try:
-            eng.set_problem(self.K, self.omega)
-            reps = 1
-            prev = None
-            chosen = None
-            while reps <= 256:
+            eng.set_problem(K_cal, w_cal)
+
+            def observe(reps: int) -> np.ndarray:
                 eng.init_product_state()
                 eng.apply_layers(step_dt, 6, reps)
                 ex, ey = eng.xy_expectations()
-                cur = np.concatenate([ex, ey])
-                if prev is not None and np.max(np.abs(cur - prev)) <= tol_step:
-                    chosen = reps // 2  # the coarser of the two already agrees: error(reps/2) ~ 64 x error(reps)
-                    break
-                prev = cur
-                reps *= 2
-            if chosen is None:
-                chosen = 256
+                return np.concatenate([ex, ey])
+
+            chosen = halving_reps(observe, tol_step)
         finally:
             eng.close()
-        chosen = max(1, chosen)
+        chosen = max(1, safety * chosen)
         self._exact_reps_cache[key] = chosen
         return chosen
 
@@ -275,17 +316,31 @@ class QuantumKuramotoSolver:
         """R exp(i psi) = (1/N) sum_j (<X_j> + i <Y_j>) of the live state (reference :156-185).
 
         ``sv`` may be a complex array of 2^n amplitudes to measure instead of the live state."""
-        eng = self.engine()
-        if sv is not None:
-            eng.set_state(np.asarray(sv))
-        return eng.order_parameter()
+        if sv is None:
+            return self.engine().order_parameter()
+        with self._scratch_engine(sv) as eng:  # a pure function of sv, like the reference: the live state is untouched
+            return eng.order_parameter()
 
     def energy_expectation(self, sv=None) -> float:
         """<H> of the live state (reference :260-264)."""
-        eng = self.engine()
-        if sv is not None:
-            eng.set_state(np.asarray(sv))
-        return eng.energy()
+        if sv is None:
+            return self.engine().energy()
+        with self._scratch_engine(sv) as eng:
+            return eng.energy()
+
+    def _scratch_engine(self, sv) -> XYKEngine:
+        """A temporary single-device engine holding the external state ``sv`` (2^n amplitudes, canonical order)."""
+        sv = np.asarray(sv)
+        if sv.shape != (1 << self.n,):
+            raise ValueError(f"statevector must hold 2^n = {1 << self.n} amplitudes, got shape {sv.shape}")
+        eng = XYKEngine(self.n, dtype=self.dtype, device=self.device)
+        try:
+            eng.set_problem(self.K, self.omega)
+            eng.set_state(sv)
+        except Exception:
+            eng.close()
+            raise
+        return eng
 
     def statevector(self) -> np.ndarray:
         """Host copy of the live state in canonical (little-endian) index order."""
@@ -336,7 +391,8 @@ class QuantumKuramotoSolver:
             "dtype": self.dtype,
         }
         if self.evolution == "reference":
-            meta["exact_composition"] = {"order": 6, "reps": {str(k): v for k, v in exact_reps.items()}}
+            meta["exact_composition"] = {"order": 6, "reps": {str(k): v for k, v in exact_reps.items()},
+                                         "calibration": self.exact_calibration}
         return TrajectoryResult(times=times, R=R_history, metadata=meta)
 
     def _run_small(self, step_sizes: np.ndarray, trotter_per_step: int, exact_reps: dict[float, int]) -> np.ndarray:

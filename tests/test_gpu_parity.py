@@ -293,3 +293,108 @@ def test_auto_solve_and_upde():
     doc = REFGOLD["doc_traces_3_digits"]["upde_run_5steps_dt0.05_n4"]
     assert np.abs(np.round(np.concatenate([[Rref[0]], vals]), 3) - np.array(doc)).max() < 1.5e-3
     u.close()
+
+
+@pytest.mark.parametrize("n", [22, 24])
+def test_reference_mode_large_n_repetition_count(n):
+    """evolution="reference" above n = 20: R(t) of the calibrated 6th-order composition equals the
+    same run with doubled repetitions to 1e-9 -- for the direct halving check on the full problem and for the
+    reduced-problem proxy that larger / sharded states use."""
+    K, w = oc.random_problem(n, 4200 + n)
+    dt, nsteps = 0.1, 2
+    traces = {}
+    for kind in ("direct", "proxy"):
+        s = QuantumKuramotoSolver(n, K, w)  # default evolution="reference"
+        if kind == "proxy":
+            s._calibrate_direct_max_n = 0
+        res = s.run(nsteps * dt, dt)
+        meta = res.metadata["exact_composition"]
+        assert meta["calibration"]["kind"] == ("direct" if kind == "direct" else "reduced_problem")
+        reps = max(meta["reps"].values())
+        traces[kind] = np.asarray(res["R"])
+        # the same trajectory with twice the repetitions, straight on the engine
+        eng = s.engine()
+        eng.init_product_state()
+        R2 = [eng.order_parameter()[0]]
+        for _ in range(nsteps):
+            eng.apply_layers(dt, 6, 2 * reps)
+            R2.append(eng.order_parameter()[0])
+        s.close()
+        assert np.abs(traces[kind] - np.array(R2)).max() < R_TOL, (kind, reps)
+    assert np.abs(traces["direct"] - traces["proxy"]).max() < R_TOL
+
+
+def test_set_coupling_mid_trajectory_vs_oracle():
+    """re-parameterising K on the LIVE state (realtime-feedback tick, reference control/realtime_feedback.py:98-137):
+    two steps with K, then K scaled by 0.5 for two more steps, against the oracle applying the same sequence"""
+    n = 14
+    K, w = oc.random_problem(n, 515)
+    Kc, wc = oc.canonicalise(n, K, w)
+    u = QuantumUPDESolver(K, w, evolution="trotter")
+    got = [u.step(0.1, 3)["R_global"] for _ in range(2)]
+    u.set_coupling(0.5 * K)
+    got += [u.step(0.1, 3)["R_global"] for _ in range(2)]
+    psi_gpu = u.statevector()
+    u.close()
+    psi = oc.initial_state(wc)
+    want = []
+    for k in range(4):
+        z, p = oc.term_list(Kc if k < 2 else 0.5 * Kc, wc)
+        psi = oc.evolve_product_formula(psi, z, p, 0.1, 3, 1)
+        want.append(oc.order_parameter(psi, n)[0])
+    assert np.abs(np.array(got) - np.array(want)).max() < R_TOL
+    assert 1.0 - oc.fidelity(psi_gpu, psi) < FID_TOL
+
+
+def test_measuring_an_external_state_leaves_the_live_state_alone():
+    n = 13
+    K, w = oc.random_problem(n, 99)
+    s = QuantumKuramotoSolver(n, K, w, evolution="trotter")
+    s.prepare_initial_state()
+    s.evolve(0.1, 2)
+    R_live, _ = s.measure_order_parameter()
+    other = oc.initial_state(oc.canonicalise(n, K, w)[1])
+    R_ext, _ = s.measure_order_parameter(other)
+    assert abs(R_ext - oc.order_parameter(other, n)[0]) < 1e-12
+    assert abs(s.energy_expectation(other) - oc.energy(other, n, *oc.canonicalise(n, K, w))) < 1e-10
+    assert s.measure_order_parameter()[0] == R_live
+    s.close()
+
+
+def test_batch_config3_subset_vs_oracle():
+    """BASELINE configs[2]: 4096 independent n = 12 problems, 100 layers each; parity on a random 64-problem subset
+     against the C oracle"""
+    B, n = 4096, 12
+    Ks, ws = np.empty((B, n, n)), np.empty((B, n))
+    for b in range(B):
+        Ks[b], ws[b] = oc.random_problem(n, 20260716 + b)
+    steps = np.full(20, 0.1)
+    R = batch_run(Ks, ws, steps, 5, 1)
+    assert R.shape == (B, 21)
+    lib = ctypes.CDLL(_ORACLE_SO)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.xyo_run.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp]
+    for b in np.random.default_rng(3).choice(B, 64, replace=False):
+        Kc, wc = oc.canonicalise(n, Ks[b], ws[b])
+        Ksym = np.ascontiguousarray((Kc + Kc.T) / 2.0)
+        psi, Rref = np.zeros(2 << n), np.zeros(21)
+        lib.xyo_run(n, Ksym.ctypes.data_as(dp), wc.ctypes.data_as(dp), steps.ctypes.data_as(dp), 20, 5, 1,
+                    psi.ctypes.data_as(dp), Rref.ctypes.data_as(dp))
+        assert np.abs(R[b] - Rref).max() < R_TOL
+
+
+@pytest.mark.parametrize("n", [13, 16, 21])
+def test_tile_observables_after_evolution(n):
+    """<X_q>, <Y_q> through the shared-memory tile sweeps (n_local >= 13) in the permuted layout the passes leave behind"""
+    K, w = oc.random_problem(n, 300 + n)
+    ref = c_oracle_evolve(n, K, w, 0.2, 2, 1)
+    with XYKEngine(n) as eng:
+        eng.set_problem(*oc.canonicalise(n, K, w))
+        eng.set_engine("tiled")
+        eng.init_product_state()
+        eng.apply_layers(0.2, 1, 2)
+        ex, ey = eng.xy_expectations()
+        ez = eng.z_expectations()
+    rx, ry = oc.xy_expectations(ref, n)
+    assert np.abs(ex - rx).max() < 1e-12 and np.abs(ey - ry).max() < 1e-12
+    assert np.abs(ez - oc.z_expectations(ref, n)).max() < 1e-12
