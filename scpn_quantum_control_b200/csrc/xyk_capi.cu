@@ -411,8 +411,10 @@ void fill_desc(xyk_handle h, Program& prog, const std::vector<int>& loc2log, con
     }
 }
 
-// tuning experiments (environment overrides of the schedule compiler's defaults)
+// tuning experiments (environment overrides of the schedule compiler's defaults): compiled only into the development
+// build (-DXYK_EXPERIMENTS, `make experiments` -> tools/_build/libxyk_exp.so); the shipped library reads no environment
 void apply_env(SchedConfig& cfg) {
+#ifdef XYK_EXPERIMENTS
     if (const char* e = std::getenv("XYK_LANE_BITS")) cfg.lane_bits = std::atoi(e);
     if (const char* e = std::getenv("XYK_NEED_SHARED")) cfg.need_shared = std::atoi(e);
     if (const char* e = std::getenv("XYK_SPLIT")) cfg.split_rounds = std::atoi(e) != 0;
@@ -427,6 +429,9 @@ void apply_env(SchedConfig& cfg) {
     if (const char* e = std::getenv("XYK_UNB_LAST")) cfg.unb_last = std::atoi(e) != 0;
     if (const char* e = std::getenv("XYK_SPLIT_MIN_LEFT")) cfg.split_min_left = std::atoi(e);
     if (const char* e = std::getenv("XYK_SPLIT_MARGIN")) cfg.split_margin = std::atoi(e);
+#else
+    (void)cfg;
+#endif
 }
 
 void finish_program(xyk_handle h, Program& prog) {
@@ -484,8 +489,11 @@ PassKernel pass_kernel_fn(bool lift, bool peer, int unb) {
 }
 // 0: balanced rounds only; 1 / 2: the pass holds 1 | 5 / 2 | 4 split rounds (the schedule compiler never mixes the two)
 int desc_unbalanced(const Desc& d) {
+    int kind = 0;
+#ifdef XYK_EXPERIMENTS
     static const char* force = std::getenv("XYK_FORCE_UNB");  // experiment: always run one of the larger kernels
-    int kind = force ? std::atoi(force) : 0;
+    if (force) kind = std::atoi(force);
+#endif
     for (int r = 0; r < d.nrounds; ++r)
         if (d.rounds[r].split == 1 || d.rounds[r].split == 2) kind = d.rounds[r].split;
     return kind;
@@ -497,7 +505,7 @@ int configure_pass_kernels(xyk_handle h) {
     int occ = 0;
     XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel_fn(true, false, 0), kPassGroups << (kTB - kRB), smem));
     if (occ < 1) occ = 1;
-#ifdef XYK_TRACE
+#if defined(XYK_TRACE) && defined(XYK_EXPERIMENTS)
     if (const char* e = std::getenv("XYK_PASS_OCC")) occ = std::max(1, std::min(occ, std::atoi(e)));  // development build only
     std::fprintf(stderr, "pass kernel occupancy: %d CTAs per SM\n", occ);
 #endif
@@ -536,8 +544,12 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
     if (peer)
         for (int r = 0; r < h->world; ++r) peers.p[r] = (double2*)h->peer_buf[r][h->cur ^ 1];
     int rc;
+#ifdef XYK_EXPERIMENTS
     const char* stop_env = std::getenv("XYK_STOP_AFTER_PASS");  // debugging: run only the first k passes of a program
     const long stop_after = stop_env ? std::atol(stop_env) : -1;
+#else
+    constexpr long stop_after = -1;
+#endif
     for (size_t p = p0; p < p1; ++p) {
         if (stop_after >= 0 && (long)p >= stop_after) break;
         const PlanPass& pp = plan.passes[p];
@@ -561,24 +573,18 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
             cudaMemcpyToSymbolAsync(xyk_trace_buf, &tp, sizeof(tp), 0, cudaMemcpyHostToDevice, h->stream);
         }
 #endif
-        static const int ablate = std::getenv("XYK_ABLATE") ? std::atoi(std::getenv("XYK_ABLATE")) : 0;  // timing experiments only (wrong results)
+#ifdef XYK_EXPERIMENTS
+        static const int ablate = std::getenv("XYK_ABLATE") ? std::atoi(std::getenv("XYK_ABLATE")) : 0;  // timing experiments only (WRONG results)
         if (ablate) {
             auto d = prog.descs[p];
             if (ablate & 1) for (int r = 0; r < d.nrounds; ++r) d.rounds[r].mask = 0;
             if (ablate & 2) d.nrounds = 1;
             if (ablate & 4) d.flags &= ~kPassHasPhase;
-            if (ablate & 16) d.flags |= kPassNoPrefetch;
-            if (ablate & 32) d.flags |= kPassPfLate;
-            if (ablate & 64) d.flags |= kPassPfEvictLast;
-            if (ablate & 128) d.flags |= kPassPlainLd;
-            if (ablate & 256) {
-                d.flags |= kPassStagger;
-                static const int stns = std::getenv("XYK_STAGGER_NS") ? std::atoi(std::getenv("XYK_STAGGER_NS")) : 4000;
-                d.pad0 = stns;
-            }
             if (ablate & 8) for (int r = 0; r < d.nrounds; ++r) d.rounds[r].cta_sync = 0;
             pass_kernel_fn(true, false, desc_unbalanced(d))<<<grid, nthr, smem, h->stream>>>(in, out, d, ntiles, peers);
-        } else {
+        } else
+#endif
+        {
             pass_kernel_fn(prog.lift[p] != 0, peer, desc_unbalanced(prog.descs[p]))<<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
         }
         if (h->stats.timing_enabled) cudaEventRecord(h->pass_events[2 * p + 1], h->stream);
@@ -596,7 +602,12 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
 
 int end_program(xyk_handle h, Program& prog, size_t timed_passes) {
     const Plan& plan = prog.plan;
-    if (plan.has_trailing_phase && !std::getenv("XYK_STOP_AFTER_PASS")) {
+#ifdef XYK_EXPERIMENTS
+    const bool stopped_early = std::getenv("XYK_STOP_AFTER_PASS") != nullptr;
+#else
+    constexpr bool stopped_early = false;
+#endif
+    if (plan.has_trailing_phase && !stopped_early) {
         int rc = apply_phase(h, plan.trailing_ztau);
         if (rc) return rc;
     }
@@ -609,7 +620,11 @@ int end_program(xyk_handle h, Program& prog, size_t timed_passes) {
             cudaEventElapsedTime(&ms, h->pass_events[2 * p], h->pass_events[2 * p + 1]);
             h->stats.pass_kernel_ms += ms;
             h->stats.pass_kernel_timed++;
+#ifdef XYK_EXPERIMENTS
             static const bool dbg = std::getenv("XYK_DEBUG_PASSES") != nullptr;
+#else
+            constexpr bool dbg = false;
+#endif
             if (dbg && p < plan.passes.size()) {
                 const PlanPass& pp = plan.passes[p];
                 std::fprintf(stderr, "pass %2zu: shared=%d fuse_load=%d fuse_store=%d rounds=%zu gates=%d lift=%d  %.3f ms  %.0f GB/s\n", p, pp.n_shared,
@@ -711,8 +726,10 @@ int xy_expect_tiled_device(xyk_handle h) {
     // chunk size of the strided sweeps: 2^nb amplitudes.  256-byte chunks (nb = 4, eight new bits per sweep) unless larger
     // chunks need no more sweeps; 128-byte chunks (nine bits per sweep) run slower than one more sweep (512 copies per tile)
     int nb = 4;
+#ifdef XYK_EXPERIMENTS
     if (const char* e = std::getenv("XYK_OBS_NB")) nb = std::atoi(e);
     else
+#endif
         for (int c = 8; c > 4; --c)
             if ((rem + (12 - c) - 1) / (12 - c) <= (rem + 7) / 8) { nb = c; break; }
     const int per = 12 - nb, nsweeps = 1 + (rem + per - 1) / per;

@@ -379,7 +379,6 @@ constexpr uint32_t kPassNoPrefetch = 8u; // do not pull the next tile into L2 ah
 constexpr uint32_t kPassPfLate = 16u;     // experiment: prefetch the next tile at the start of the LAST round
 constexpr uint32_t kPassPfEvictLast = 32u; // experiment: prefetch with an L2 evict_last policy
 constexpr uint32_t kPassPlainLd = 64u;    // experiment: plain ld.global instead of ld.global.cs
-constexpr uint32_t kPassStagger = 128u;   // experiment: CTAs that share an SM start a third of a tile period apart
 
 template <int TB, int RB>
 struct PassDesc {

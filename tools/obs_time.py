@@ -1,6 +1,9 @@
 """Development aid: wall time (synchronised) of the product-state init and of one R(t) evaluation at n."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _devlib import use_dev_library  # noqa: E402
+use_dev_library()
 import numpy as np
 from oracle import xy_oracle as oc  # problem generator only
 from scpn_quantum_control_b200.engine import XYKEngine

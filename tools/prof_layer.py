@@ -3,6 +3,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _devlib import use_dev_library  # noqa: E402
+use_dev_library()
 from oracle import xy_oracle as oc  # noqa: E402  (problem generator only)
 from scpn_quantum_control_b200.engine import XYKEngine  # noqa: E402
 

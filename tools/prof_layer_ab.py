@@ -1,9 +1,9 @@
 """A/B timing of two builds of libxyk.so on the same box: XYK_LIB_AB=<path> selects the library (development aid)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from scpn_quantum_control_b200 import _lib
-if os.environ.get("XYK_LIB_AB"):
-    _lib.LIB_PATH = os.path.abspath(os.environ["XYK_LIB_AB"])
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _devlib import use_dev_library  # noqa: E402
+use_dev_library()
 from oracle import xy_oracle as oc  # noqa: E402
 from scpn_quantum_control_b200.engine import XYKEngine  # noqa: E402
 

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from scpn_quantum_control_b200 import _lib  # noqa: E402
 
-_lib.LIB_PATH = os.path.join(ROOT, "tools", "_build", "libxyk_trace.so")
+_lib.LIB_PATH = os.path.join(ROOT, "tools", "_build", "libxyk_trace.so")  # make -C scpn_quantum_control_b200/csrc trace
 from oracle import xy_oracle as oc  # noqa: E402  (problem generator only)
 from scpn_quantum_control_b200.engine import XYKEngine  # noqa: E402
 
