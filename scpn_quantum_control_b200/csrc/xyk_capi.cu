@@ -537,7 +537,7 @@ size_t g_trace_words = 0;
 int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
     const Plan& plan = prog.plan;
     const uint64_t ntiles = 1ull << (h->nlocal - kTB);
-    const int grid = (int)std::min<uint64_t>((ntiles + kPassGroups - 1) / kPassGroups, (uint64_t)h->pass_grid);
+    const int grid = (int)std::min<uint64_t>(ntiles, (uint64_t)h->pass_grid);  // few tiles: one per SM (group 0 of each CTA)
     const int smem = kPassGroups * (int)tile_bytes<kTB>();
     const int nthr = kPassGroups << (kTB - kRB);
     PeerPtrs peers{};
@@ -1408,17 +1408,33 @@ int xyk_energy(xyk_handle h, double* E) {
 int xyk_run(xyk_handle h, const double* step_sizes, int m, int reps, int order, double* R_out) {
     if (!h || !R_out || (m > 0 && !step_sizes)) return XYK_ERR_INVALID;
     XYK_CHECK(h, m >= 0, XYK_ERR_INVALID, "m must be >= 0");
+    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "xyk_run drives a single-device state (sharded states are driven by the host)");
     int rc = xyk_init_product_state(h);
     if (rc) return rc;
-    rc = xyk_order_parameter(h, &R_out[0], nullptr);
-    if (rc) return rc;
-    for (int s = 0; s < m; ++s) {
+    // the whole trajectory is enqueued without a host round trip: R(t) stays on the device until the end
+    double* d_R = nullptr;
+    XYK_CUDA(h, cudaMalloc(&d_R, sizeof(double) * (size_t)(m + 1)));
+    auto record = [&](int s) -> int {
+        int r = xy_expect_device(h);
+        if (r) return r;
+        order_param_kernel<<<1, 32, 0, h->stream>>>(h->d_out, h->n, d_R + s);
+        h->stats.kernel_launches++;
+        return XYK_OK;
+    };
+    rc = record(0);
+    for (int s = 0; s < m && rc == XYK_OK; ++s) {
         rc = xyk_apply_layers(h, step_sizes[s], order, reps);
-        if (rc) return rc;
-        rc = xyk_order_parameter(h, &R_out[s + 1], nullptr);
-        if (rc) return rc;
+        if (rc == XYK_OK) rc = record(s + 1);
     }
-    return XYK_OK;
+    if (rc == XYK_OK) {
+        cudaError_t e = cudaMemcpyAsync(R_out, d_R, sizeof(double) * (size_t)(m + 1), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, XYK_ERR_CUDA, std::string("xyk_run: ") + cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(d_R);
+    return rc;
 }
 
 int xyk_get_state(xyk_handle h, void* dst, int is_device) {

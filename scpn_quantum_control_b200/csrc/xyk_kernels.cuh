@@ -337,6 +337,21 @@ __global__ void xy_finalize_kernel(const double2* __restrict__ partial, int nblo
     }
 }
 
+// R = |sum_q (<X_q> + i <Y_q>)| / n from the finalized expectations (xy[2q], xy[2q+1]); summed in qubit order by one thread,
+// exactly like the host loop of xyk_order_parameter (reference: phase/xy_kuramoto.py:173,183-184)
+__global__ void order_param_kernel(const double* __restrict__ xy, int n, double* __restrict__ R) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double zr = 0.0, zi = 0.0;
+        for (int q = 0; q < n; ++q) {
+            zr += xy[2 * q];
+            zi += xy[2 * q + 1];
+        }
+        zr /= n;
+        zi /= n;
+        *R = sqrt(zr * zr + zi * zi);
+    }
+}
+
 struct PermSpec {
     uint8_t dst_of_src[kMaxQ];  // source physical bit b -> destination physical bit
     int32_t nlocal;
@@ -953,13 +968,13 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     uint32_t tile_parity = 0;
     // tile indices fit 32 bits (at most 2^31 local amplitudes)
     const uint32_t tstride = gridDim.x * NG;   // tiles between two consecutive tiles of a group
-    const uint32_t tfirst = blockIdx.x * NG + grp;
+    const uint32_t tfirst = grp * gridDim.x + blockIdx.x;   // group 0 of every CTA first: few tiles spread over all SMs
     const uint32_t ntile32 = (uint32_t)ntiles;
     if ((flags & kPassFuseLoad) && tid == 0 && tfirst < ntile32) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)tfirst << TB), mbar_u32);
 
     // every group of a CTA runs the same number of iterations: the token ring needs all of them (a group without a tile left
     // only passes the token on)
-    for (uint32_t t = tfirst; t - grp < ntile32; t += tstride) {  // as long as group 0 of this CTA has a tile
+    for (uint32_t t = tfirst; t - grp * gridDim.x < ntile32; t += tstride) {  // as long as group 0 of this CTA has a tile
         if (NG > 1 && t >= ntile32) {
             for (int k = 0; k < nr; ++k) {
                 token_acquire(1);

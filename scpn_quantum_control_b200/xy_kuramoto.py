@@ -256,6 +256,11 @@ class QuantumKuramotoSolver:
             return self.trotter_order, trotter_steps
         return 6, self._calibrated_exact_reps(step_dt)
 
+    def _uniform_formula(self, step_sizes: np.ndarray, trotter_steps: int) -> tuple[int, int] | None:
+        """(order, reps) when every interval of the grid runs the same formula, else None."""
+        forms = {self._formula(float(s), trotter_steps) for s in np.unique(np.round(step_sizes, 15))}
+        return forms.pop() if len(forms) == 1 else None
+
     def _calibrated_exact_reps(self, step_dt: float, nsteps: int = 1) -> int:
         """Smallest power-of-two repetition count of the 6th-order composition whose observables
         over one interval agree with the doubled count to ``exact_tol / nsteps`` (a-posteriori
@@ -373,6 +378,10 @@ class QuantumKuramotoSolver:
 
         if self.n <= _SMALL_N and self.dtype == "complex128" and not self.distributed:
             R_history = self._run_small(step_sizes, trotter_per_step, exact_reps)
+        elif not self.distributed and self._uniform_formula(step_sizes, trotter_per_step) is not None:
+            # one C call enqueues the whole trajectory (state preparation, layers, R(t) on the device, one read-back)
+            order, reps = self._uniform_formula(step_sizes, trotter_per_step)
+            R_history = self.engine().run(step_sizes, reps, order)
         else:
             eng = self.engine()
             eng.init_product_state()
