@@ -123,6 +123,11 @@ int xyk_energy(xyk_handle h, double *E);
 /* sum_k |psi_k|^2 over this shard */
 int xyk_norm2(xyk_handle h, double *norm2);
 
+/* psi <- prod_q Ry_q(angles[q]) psi on the live state (Ry(t) = [[cos t/2, -sin t/2], [sin t/2, cos t/2]]); angles of
+ * exactly 0 are skipped.  Single-GPU handles.  Replaces: the per-qubit `qc.ry(...)` correction layer that
+ * RealtimeSyncFeedbackController applies with Statevector.evolve (control/realtime_feedback.py:209-227). */
+int xyk_apply_ry(xyk_handle h, const double *angles);
+
 /* The whole run() loop on the device: init, R[0], then for each step_sizes[s]: evolve, R[s+1].
  * Replaces: QuantumKuramotoSolver.run hot loop (xy_kuramoto.py:236-248). Single GPU only. */
 int xyk_run(xyk_handle h, const double *step_sizes, int m, int reps, int order, double *R_out);

@@ -1405,6 +1405,27 @@ int xyk_energy(xyk_handle h, double* E) {
     return XYK_OK;
 }
 
+int xyk_apply_ry(xyk_handle h, const double* angles) {
+    if (!h || !angles) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "single-qubit rotations of a sharded state are not supported");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    const uint64_t half = 1ull << (h->nlocal - 1);
+    for (int q = 0; q < h->n; ++q) {
+        XYK_CHECK(h, std::isfinite(angles[q]), XYK_ERR_INVALID, "angles must be finite");
+        if (angles[q] == 0.0) continue;
+        const double c = std::cos(angles[q] / 2.0), s = std::sin(angles[q] / 2.0);
+        if (h->dtype == 0)
+            ry_gate_kernel<double><<<grid_for(h, half, 256), 256, 0, h->stream>>>((double2*)h->buf[h->cur], h->nlocal, h->perm[q], c, s);
+        else
+            ry_gate_kernel<float><<<grid_for(h, half, 256), 256, 0, h->stream>>>((float2*)h->buf[h->cur], h->nlocal, h->perm[q], c, s);
+        h->stats.kernel_launches++;
+        h->stats.state_sweeps++;
+    }
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
 int xyk_run(xyk_handle h, const double* step_sizes, int m, int reps, int order, double* R_out) {
     if (!h || !R_out || (m > 0 && !step_sizes)) return XYK_ERR_INVALID;
     XYK_CHECK(h, m >= 0, XYK_ERR_INVALID, "m must be >= 0");

@@ -169,6 +169,24 @@ __global__ void pair_gate_kernel(typename cplx<real>::type* __restrict__ psi, in
     }
 }
 
+// (a, b) = (psi[..0_pos..], psi[..1_pos..]) <- (c a - s b, s a + c b): Ry(theta) with c = cos(theta/2), s = sin(theta/2)
+template <typename real>
+__global__ void ry_gate_kernel(typename cplx<real>::type* __restrict__ psi, int nlocal, int pos, double c, double s) {
+    const uint64_t half = 1ull << (nlocal - 1);
+    const uint64_t m = 1ull << pos;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < half; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = insert_zero64(t, pos);
+        typename cplx<real>::type a = psi[k], b = psi[k | m];
+        const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+        a.x = (real)(c * ar - s * br);
+        a.y = (real)(c * ai - s * bi);
+        b.x = (real)(s * ar + c * br);
+        b.y = (real)(s * ai + c * bi);
+        psi[k] = a;
+        psi[k | m] = b;
+    }
+}
+
 // partial[blockIdx.x] = (sum_k Re conj(psi_k) psi_{k|m}, sum_k Im ...) over k with bit `pos` clear
 // (scpn_quantum_engine/src/pauli.rs:195-211, without the factor 2)
 template <typename real>

@@ -129,6 +129,13 @@ class XYKEngine:
         self._check(self._lib.xyk_norm2(self._h, byref(v)))
         return v.value
 
+    def apply_ry(self, angles: np.ndarray) -> None:
+        """psi <- prod_q Ry_q(angles[q]) psi on the live state."""
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        if a.shape != (self.n,):
+            raise ValueError(f"angles must have shape ({self.n},), got {a.shape}")
+        self._check(self._lib.xyk_apply_ry(self._h, _dptr(a)))
+
     def run(self, step_sizes: np.ndarray, reps: int, order: int) -> np.ndarray:
         steps = np.ascontiguousarray(step_sizes, dtype=np.float64)
         R = np.zeros(steps.shape[0] + 1)
