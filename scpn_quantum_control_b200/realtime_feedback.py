@@ -93,14 +93,12 @@ def feedback_policy_numpy(r_values, target_r: float, deadband: float, base_gain:
     _require_positive(base_gain, "base_gain", allow_zero=True)
     if not np.isfinite(max_gain) or max_gain < 1.0:
         raise ValueError("max_gain must be finite and at least 1.0")
-    errors = target_r - r
-    actions = np.zeros(r.shape, dtype=np.int32)
-    gains = np.ones(r.shape, dtype=np.float64)
-    low, high = errors > deadband, errors < -deadband
-    actions[low], actions[high] = 1, -1
-    gains[low] = np.minimum(1.0 + base_gain * errors[low], max_gain)
-    gains[high] = np.clip(1.0 + base_gain * errors[high], 1.0 / max_gain, 1.0)
-    return actions, gains, errors.astype(np.float64)
+    errors = np.asarray(target_r - r, dtype=np.float64)
+    raw = 1.0 + base_gain * errors
+    below, above = errors > deadband, errors < -deadband  # too little / too much synchrony
+    actions = below.astype(np.int32) - above.astype(np.int32)
+    gains = np.where(below, np.minimum(raw, max_gain), np.where(above, np.clip(raw, 1.0 / max_gain, 1.0), 1.0))
+    return actions, gains.astype(np.float64), errors
 
 
 def _sample_axis(expectations: np.ndarray, shots: int, rng: np.random.Generator) -> np.ndarray:

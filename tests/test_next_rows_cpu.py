@@ -1,0 +1,61 @@
+"""CPU tests of the SURVEY 8(f) "next" rows: host logic of the feedback controller mirror against the oracle's
+restatement of the reference policy (control/realtime_feedback.py:316-341), and the next-rows oracle against itself
+(XXZ Mode T converges to Mode E, delta = 0 reduces to the path oracle, Floquet with zero drive = static exact run)."""
+import numpy as np
+import pytest
+
+from oracle import xy_oracle as oc
+from oracle import xy_oracle_next as on
+from scpn_quantum_control_b200.realtime_feedback import RealtimeFeedbackConfig, feedback_policy_numpy
+
+
+def test_feedback_policy_matches_oracle_scalar_policy():
+    rng = np.random.default_rng(5)
+    r = np.concatenate([rng.uniform(0, 1, 200), [0.75, 0.71, 0.79, 0.0, 1.0]])
+    for (t, d, g, m) in [(0.75, 0.04, 0.8, 2.0), (0.5, 0.0, 3.0, 1.5), (0.9, 0.2, 0.0, 1.0)]:
+        a, gains, e = feedback_policy_numpy(r, t, d, g, m)
+        assert a.dtype == np.int32 and gains.dtype == np.float64
+        for k in range(r.shape[0]):
+            code, gain, err = on.feedback_policy(float(r[k]), t, d, g, m)
+            assert (int(a[k]), float(gains[k]), float(e[k])) == (code, gain, err)
+
+
+def test_feedback_config_validation_messages():
+    with pytest.raises(ValueError, match=r"target_r must be finite and in \[0.0, 1.0\]"):
+        RealtimeFeedbackConfig(target_r=1.5)
+    with pytest.raises(ValueError, match="base_dt must be finite and positive"):
+        RealtimeFeedbackConfig(base_dt=0.0)
+    with pytest.raises(ValueError, match="trotter_steps must be a positive integer"):
+        RealtimeFeedbackConfig(trotter_steps=0)
+    with pytest.raises(ValueError, match="max_gain must be finite and at least 1.0"):
+        RealtimeFeedbackConfig(max_gain=0.5)
+    with pytest.raises(ValueError, match="feedback_correction_sign must be either -1.0 or 1.0"):
+        RealtimeFeedbackConfig(feedback_correction_sign=0.5)
+    with pytest.raises(ValueError, match="r_values must contain only finite values"):
+        feedback_policy_numpy(np.array([np.nan]), 0.5, 0.1, 1.0, 2.0)
+
+
+def test_xxz_oracle_reduces_and_converges():
+    n = 6
+    K, w = oc.random_problem(n, 11)
+    t0, R0 = oc.run(n, K, w, 0.3, 0.1, 4, order=2, mode="T")
+    t1, R1 = on.run_xxz(n, K, w, 0.0, 0.3, 0.1, 4, order=2, mode="T")
+    assert np.array_equal(t0, t1) and np.max(np.abs(R0 - R1)) < 1e-14
+    _, RE = on.run_xxz(n, K, w, 0.7, 0.3, 0.1, mode="E")
+    err = [np.max(np.abs(on.run_xxz(n, K, w, 0.7, 0.3, 0.1, reps, order=2, mode="T")[1] - RE)) for reps in (2, 4, 8)]
+    assert err[0] > err[1] > err[2] and err[1] / err[2] > 3.5  # second order
+
+
+def test_floquet_oracle_zero_drive_is_static_exact_evolution():
+    n = 4
+    K = oc.paper27_K(n)
+    w = oc.OMEGA_N_16[:n]
+    out, psi = on.floquet_evolve(K / K.max(), w, 0.45, 0.0, 2.0, 1, 6, return_state=True)
+    assert np.allclose(out["drive_signal"], 0.45)
+    Ks = 0.45 * K / K.max()
+    ref = np.full(1 << n, 0.25, dtype=np.complex128)
+    H = oc.hamiltonian_sparse(Ks, w)
+    for _ in range(6):
+        ref = oc.exact_step(ref, H, (2 * np.pi / 2.0) / 6)
+    assert 1 - oc.fidelity(psi, ref) < 1e-12
+    assert out["R_values"][0] == pytest.approx(1.0)
