@@ -73,12 +73,24 @@ int xyk_set_option(xyk_handle h, int option, int64_t value);
  * (bridge/knm_hamiltonian.py:141-217).  May be called again at any time to re-parameterise
  * the couplings without touching the state (control/realtime_feedback.py:98-137). */
 int xyk_set_problem(xyk_handle h, const double *K, const double *omega);
+/* XXZ anisotropy: H = -sum K_ij (XX + YY + delta ZZ) - sum omega_i Z_i.  Replaces: knm_to_xxz_hamiltonian(K, omega, delta)
+ * (bridge/knm_hamiltonian.py:141-206; |delta| <= 1e-15 drops the ZZ terms like the reference).  The gate-by-gate engine
+ * applies XX.YY then ZZ per pair in the reference's term order; the tiled engine groups all ZZ terms with the diagonal
+ * Z phase of each (half) layer -- the same operator for orders >= 2 up to the splitting error of the formula, and
+ * exact under the 6th-order composition used for evolution="reference".  Single-GPU handles. */
+int xyk_set_problem_xxz(xyk_handle h, const double *K, const double *omega, double delta);
+
 /* number of retained pair terms / Z terms of the current problem */
 int xyk_term_counts(xyk_handle h, int *n_pairs, int *n_z);
 
 /* psi0 = prod_i Ry(omega_i mod 2pi)|0>, generated on the device.
  * Replaces: xy_kuramoto.py:236-242 (Statevector.from_instruction of the Ry circuit). */
 int xyk_init_product_state(xyk_handle h);
+
+/* |psi> = prod_q Ry(angles[q])|0>, qubit 0 = least significant bit; no problem needs to be set.  angles = 0: |0...0>
+ * (Statevector.from_label("0" * n), scripts/bench_s2_scaling_lite.py:262), angles = pi/2: |+>^n (the Floquet drive's
+ * start, phase/floquet_kuramoto.py:131).  Works on sharded handles (every rank writes its shard). */
+int xyk_init_product_angles(xyk_handle h, const double *angles);
 
 /* Evolve one grid interval `delta` with `reps` repetitions of the product formula of `order`:
  *   order 1 = LieTrotter, 2 = SuzukiTrotter(order=2) (Qiskit term order), 4 / 6 = Suzuki
@@ -127,6 +139,15 @@ int xyk_norm2(xyk_handle h, double *norm2);
  * exactly 0 are skipped.  Single-GPU handles.  Replaces: the per-qubit `qc.ry(...)` correction layer that
  * RealtimeSyncFeedbackController applies with Statevector.evolve (control/realtime_feedback.py:209-227). */
 int xyk_apply_ry(xyk_handle h, const double *angles);
+
+/* psi <- exp(-i H dt) psi to `tol` (per amplitude, in the expansion coefficients) WITHOUT a product formula: Chebyshev
+ * expansion of the propagator, one fused H.phi sweep per term (all pair terms summed in one kernel; XXZ anisotropy
+ * included), Bessel coefficients J_k(E |dt|) on the host, E = 2 sum |K| (+ |delta| sum |K|) + sum |omega|.  Needs room for
+ * three state vectors.  *terms_used (may be NULL) returns the number of Chebyshev terms.
+ * Replaces: the exact sibling of the path, classical_exact_evolution's expm_multiply step
+ * (hardware/classical.py:201-208, hardware/fast_classical.py:35-97) -- and gives the engine a second, independent
+ * route to what Statevector.evolve returns under the reference's pinned Qiskit (Mode E).  Single-GPU, complex128. */
+int xyk_exact_step(xyk_handle h, double dt, double tol, int *terms_used);
 
 /* The whole run() loop on the device: init, R[0], then for each step_sizes[s]: evolve, R[s+1].
  * Replaces: QuantumKuramotoSolver.run hot loop (xy_kuramoto.py:236-248). Single GPU only. */

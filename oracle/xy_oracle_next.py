@@ -156,6 +156,30 @@ def layer_order2_xxz(psi, n, z_terms, pair_terms, tau):
     return psi
 
 
+def layer_order2_xxz_grouped(psi, n, z_terms, pair_terms, tau):
+    """The tiled engine's splitting for delta != 0 (include/xyk.h, xyk_set_problem_xxz): all diagonal terms (Z and ZZ)
+    grouped at both ends of the symmetric pair sweep -- D(tau/2) P_fwd P_bwd D(tau/2).  Not the reference's term order
+    (that is layer_order2_xxz); the same exact limit."""
+    half = tau / 2.0
+
+    def diag(t):
+        oc.apply_z_phase(psi, z_terms, t)
+        for (i, j, k, kz) in pair_terms:
+            if kz != 0.0:
+                apply_zz(psi, n, i, j, kz * t)
+
+    diag(half)
+    if pair_terms:
+        for (i, j, k, kz) in pair_terms[:-1]:
+            oc.apply_pair(psi, i, j, 2.0 * k * half)
+        i, j, k, kz = pair_terms[-1]
+        oc.apply_pair(psi, i, j, 2.0 * k * tau)
+        for (i, j, k, kz) in reversed(pair_terms[:-1]):
+            oc.apply_pair(psi, i, j, 2.0 * k * half)
+    diag(half)
+    return psi
+
+
 def hamiltonian_sparse_xxz(K, omega, delta):
     """H = -sum K_ij (XX + YY + delta ZZ) - sum omega_i Z_i as scipy.sparse (knm_hamiltonian.py:209-217)."""
     import scipy.sparse as sp

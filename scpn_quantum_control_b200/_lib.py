@@ -73,7 +73,10 @@ PROTOTYPES = {
     "xyk_correlation_matrix_xy": (c_int, [c_void_p, POINTER(c_double)]),
     "xyk_energy": (c_int, [c_void_p, POINTER(c_double)]),
     "xyk_norm2": (c_int, [c_void_p, POINTER(c_double)]),
+    "xyk_set_problem_xxz": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), c_double]),
+    "xyk_exact_step": (c_int, [c_void_p, c_double, c_double, POINTER(c_int)]),
     "xyk_apply_ry": (c_int, [c_void_p, POINTER(c_double)]),
+    "xyk_init_product_angles": (c_int, [c_void_p, POINTER(c_double)]),
     "xyk_run": (c_int, [c_void_p, POINTER(c_double), c_int, c_int, c_int, POINTER(c_double)]),
     "xyk_get_state": (c_int, [c_void_p, c_void_p, c_int]),
     "xyk_set_state": (c_int, [c_void_p, c_void_p, c_int]),

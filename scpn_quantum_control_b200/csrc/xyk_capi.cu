@@ -74,6 +74,9 @@ struct xyk_handle_s {
     int pass_grid = 0;
     // scratch
     double2* d_tab = nullptr;     // 3 x 2^11 phase tables
+    double zz_delta = 0.0;        // XXZ anisotropy (0: XY model)
+    double* d_J = nullptr;        // n x n couplings K_ij * delta of the ZZ terms (logical indices)
+    double2* d_zztab = nullptr;   // 2^12 low-bit factors of the fused ZZ diagonal
     double* d_partial = nullptr;  // reduction partials
     double* d_out = nullptr;      // reduced values
     double* h_out = nullptr;      // pinned staging
@@ -149,16 +152,18 @@ bool perm_is_identity(xyk_handle h) {
     return true;
 }
 
-// |psi0> = prod_q Ry(omega_q mod 2 pi)|0> in the current layout: three chunk tables built on the host
+// |psi0> = prod_q Ry(theta_q)|0> in the current layout (theta_q = omega_q mod 2 pi when `angles` is null): three chunk
+// tables built on the host
 template <typename real>
-int launch_init(xyk_handle h) {
+int launch_init(xyk_handle h, const double* angles = nullptr) {
     const double two_pi = 2.0 * M_PI;
     std::vector<double> cq(h->n), sq(h->n);
     for (int q = 0; q < h->n; ++q) {
-        double a = std::fmod(h->omega[q], two_pi);  // Python's % : result has the sign of the modulus
-        if (a < 0.0) a += two_pi;
+        double a = angles ? angles[q] : std::fmod(h->omega[q], two_pi);  // Python's % : result has the sign of the modulus
+        if (!angles && a < 0.0) a += two_pi;
         cq[q] = std::cos(a / 2.0);
         sq[q] = std::sin(a / 2.0);
+        if (angles && a == 0.0) sq[q] = 0.0;
     }
     std::vector<int> log_of_bit(h->n, -1);  // logical qubit on physical bit b
     for (int q = 0; q < h->n; ++q) log_of_bit[h->perm[q]] = q;
@@ -237,6 +242,41 @@ int apply_phase(xyk_handle h, double tau) {
     return XYK_OK;
 }
 
+// XXZ: exp(+i t sum_{i<j} K_ij delta Z_i Z_j) on the whole state in the current layout (one sweep)
+int apply_zz_diag(xyk_handle h, double t) {
+    if (h->zz_delta == 0.0 || t == 0.0 || h->pairs.empty()) return XYK_OK;
+    ZZSpec S{};
+    S.nbits = h->n;
+    S.nlocal = h->nlocal;
+    S.rank = h->rank;
+    S.LB = std::min(h->nlocal, 12);
+    S.t = t;
+    for (int q = 0; q < h->n; ++q) S.log_of_bit[h->perm[q]] = q;
+    zz_low_table_kernel<<<16, 256, 0, h->stream>>>(h->d_zztab, h->d_J, h->n, S);
+    const uint64_t nblk = 1ull << (h->nlocal - S.LB);
+    const int grid = (int)std::min<uint64_t>(nblk, (uint64_t)h->sm_count * 8);
+    if (h->dtype == 0)
+        zz_diag_kernel<double><<<grid, 256, 0, h->stream>>>((double2*)h->buf[h->cur], h->d_zztab, h->d_J, h->n, S);
+    else
+        zz_diag_kernel<float><<<grid, 256, 0, h->stream>>>((float2*)h->buf[h->cur], h->d_zztab, h->d_J, h->n, S);
+    h->stats.kernel_launches += 2;
+    h->stats.state_sweeps += 1;
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
+// XXZ, gate-by-gate engine: the ZZ term of one pair right after its XX, YY terms (the reference's term order)
+int apply_zz_simple(xyk_handle h, int i, int j, double theta) {
+    const double c = std::cos(theta), s = std::sin(theta);
+    if (h->dtype == 0)
+        zz_gate_kernel<double><<<grid_for(h, 1ull << h->nlocal, 256), 256, 0, h->stream>>>((double2*)h->buf[h->cur], h->nlocal, h->perm[i], h->perm[j], c, s);
+    else
+        zz_gate_kernel<float><<<grid_for(h, 1ull << h->nlocal, 256), 256, 0, h->stream>>>((float2*)h->buf[h->cur], h->nlocal, h->perm[i], h->perm[j], c, s);
+    h->stats.kernel_launches++;
+    h->stats.state_sweeps++;
+    return XYK_OK;
+}
+
 int apply_pair_simple(xyk_handle h, int i, int j, double phi) {
     const int pi = h->perm[i], pj = h->perm[j];
     XYK_CHECK(h, pi < h->nlocal && pj < h->nlocal, XYK_ERR_UNSUPPORTED,
@@ -261,6 +301,10 @@ int run_segments_simple(xyk_handle h, const std::vector<Segment>& segs) {
         for (const auto& g : s.gates) {
             rc = apply_pair_simple(h, g.i, g.j, g.phi);
             if (rc) return rc;
+            if (h->zz_delta != 0.0) {  // g.phi = 2 K_ij tau: the ZZ term -K_ij delta Z_i Z_j evolves by exp(+i K_ij delta tau Z_i Z_j)
+                rc = apply_zz_simple(h, g.i, g.j, 0.5 * g.phi * h->zz_delta);
+                if (rc) return rc;
+            }
         }
     }
     XYK_CUDA(h, cudaGetLastError());
@@ -557,6 +601,10 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
             rc = apply_phase(h, pp.ztau);
             if (rc) return rc;
         }
+        if (pp.has_phase) {  // XXZ: all ZZ terms ride with the diagonal phase (grouped-diagonal splitting)
+            rc = apply_zz_diag(h, pp.ztau);
+            if (rc) return rc;
+        }
         const double2* in = (const double2*)h->buf[h->cur];
         double2* out = (double2*)h->buf[h->cur ^ 1];
         if (h->stats.timing_enabled) {
@@ -609,6 +657,8 @@ int end_program(xyk_handle h, Program& prog, size_t timed_passes) {
 #endif
     if (plan.has_trailing_phase && !stopped_early) {
         int rc = apply_phase(h, plan.trailing_ztau);
+        if (rc) return rc;
+        rc = apply_zz_diag(h, plan.trailing_ztau);
         if (rc) return rc;
     }
     if (h->stats.timing_enabled) {
@@ -1070,6 +1120,8 @@ int xyk_create(int n_qubits, int dtype, int device, int world_size, int rank, xy
     }
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_tab, sizeof(double2) * 3 * kTabStride) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_J, sizeof(double) * kMaxQ * kMaxQ) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_zztab, sizeof(double2) * 4096) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_partial, sizeof(double) * kPartialDoubles) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_out, sizeof(double) * 4096) == cudaSuccess;
     ok = ok && cudaMallocHost(&h->h_out, sizeof(double) * 8192) == cudaSuccess;
@@ -1093,6 +1145,8 @@ int xyk_destroy(xyk_handle h) {
     for (int b = 0; b < 2; ++b)
         if (h->buf[b]) cudaFree(h->buf[b]);
     if (h->d_tab) cudaFree(h->d_tab);
+    if (h->d_J) cudaFree(h->d_J);
+    if (h->d_zztab) cudaFree(h->d_zztab);
     if (h->d_partial) cudaFree(h->d_partial);
     if (h->d_out) cudaFree(h->d_out);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -1140,6 +1194,23 @@ int xyk_set_problem(xyk_handle h, const double* K, const double* omega) {
     h->problem_version++;
     h->programs.clear();
     h->shard_cache.clear();
+    h->zz_delta = 0.0;
+    return XYK_OK;
+}
+
+int xyk_set_problem_xxz(xyk_handle h, const double* K, const double* omega, double delta) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, std::isfinite(delta), XYK_ERR_INVALID, "delta must be finite");
+    XYK_CHECK(h, h->world == 1 || std::fabs(delta) <= kSparsityEps, XYK_ERR_UNSUPPORTED, "XXZ anisotropy on a sharded state is not supported");
+    int rc = xyk_set_problem(h, K, omega);
+    if (rc) return rc;
+    if (std::fabs(delta) <= kSparsityEps) return XYK_OK;  // the reference drops the ZZ terms below the sparsity threshold
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    std::vector<double> J(h->Ksym);
+    for (double& v : J) v *= delta;
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));  // a ZZ sweep in flight still reads the previous table
+    XYK_CUDA(h, cudaMemcpy(h->d_J, J.data(), sizeof(double) * J.size(), cudaMemcpyHostToDevice));
+    h->zz_delta = delta;
     return XYK_OK;
 }
 
@@ -1158,6 +1229,17 @@ int xyk_init_product_state(xyk_handle h) {
     // keep global bits where they are, local qubits in canonical order
     for (int q = 0; q < h->n; ++q) h->perm[q] = q;
     int rc = h->dtype == 0 ? launch_init<double>(h) : launch_init<float>(h);
+    if (rc) return rc;
+    h->state_valid = true;
+    return XYK_OK;
+}
+
+int xyk_init_product_angles(xyk_handle h, const double* angles) {
+    if (!h || !angles) return XYK_ERR_INVALID;
+    for (int q = 0; q < h->n; ++q) XYK_CHECK(h, std::isfinite(angles[q]), XYK_ERR_INVALID, "angles must be finite");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    for (int q = 0; q < h->n; ++q) h->perm[q] = q;
+    int rc = h->dtype == 0 ? launch_init<double>(h, angles) : launch_init<float>(h, angles);
     if (rc) return rc;
     h->state_valid = true;
     return XYK_OK;
@@ -1391,6 +1473,7 @@ int xyk_correlation_matrix_xy(xyk_handle h, double* C) {
 int xyk_energy(xyk_handle h, double* E) {
     if (!h || !E) return XYK_ERR_INVALID;
     XYK_CHECK(h, h->have_problem, XYK_ERR_STATE, "no problem set");
+    XYK_CHECK(h, h->zz_delta == 0.0, XYK_ERR_UNSUPPORTED, "energy of the XXZ model (ZZ correlations) is not implemented");
     const int n = h->n;
     std::vector<double> C((size_t)n * n), z(n);
     int rc = xyk_correlation_matrix_xy(h, C.data());
@@ -1423,6 +1506,101 @@ int xyk_apply_ry(xyk_handle h, const double* angles) {
         h->stats.state_sweeps++;
     }
     XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
+int xyk_exact_step(xyk_handle h, double dt, double tol, int* terms_used) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->have_problem, XYK_ERR_STATE, "no problem set");
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "the Chebyshev step runs on a single-device state");
+    XYK_CHECK(h, h->dtype == 0, XYK_ERR_UNSUPPORTED, "the Chebyshev step needs a complex128 state");
+    XYK_CHECK(h, std::isfinite(dt) && std::isfinite(tol) && tol > 0.0, XYK_ERR_INVALID, "dt must be finite and tol positive");
+    if (terms_used) *terms_used = 0;
+    if (dt == 0.0) return XYK_OK;
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_alt(h);
+    if (rc) return rc;
+    // spectral bound: ||K (XX + YY)|| = 2 |K|, ||K delta ZZ|| = |K delta|, ||w Z|| = |w|
+    double E = 0.0;
+    for (const auto& p : h->pairs) E += (2.0 + std::fabs(h->zz_delta)) * std::fabs(p.k);
+    for (const auto& z : h->zterms) E += std::fabs(z.w);
+    if (E == 0.0) return XYK_OK;  // H = 0
+    E *= 1.0 + 1e-9;
+    const double x = E * std::fabs(dt);
+    // exp(-i H dt) = sum_k c_k T_k(H / E),  c_k = (2 - [k = 0]) (-i sgn dt)^k J_k(E |dt|)
+    std::vector<double> J;
+    for (int k = 0; k < 100000; ++k) {
+        J.push_back(std::cyl_bessel_j((double)k, x));
+        if (k > x + 2 && std::fabs(J[k]) < 0.1 * tol && std::fabs(J[k - 1]) < 0.1 * tol) break;
+    }
+    const int nterms = (int)J.size();
+    auto coef = [&](int k) {
+        const double mag = (k == 0 ? 1.0 : 2.0) * J[k];
+        const int q = k & 3;  // (-i s)^k, s = sgn(dt)
+        const double sg = dt > 0 ? 1.0 : -1.0;
+        switch (q) {
+            case 0: return make_double2(mag, 0.0);
+            case 1: return make_double2(0.0, -sg * mag);
+            case 2: return make_double2(-mag, 0.0);
+            default: return make_double2(0.0, sg * mag);
+        }
+    };
+    std::vector<HPair> hp;
+    for (const auto& p : h->pairs) hp.push_back({1ull << h->perm[p.i], 1ull << h->perm[p.j], p.k, p.k * h->zz_delta});
+    std::vector<double> wbit(h->n, 0.0);
+    for (const auto& z : h->zterms) wbit[h->perm[z.i]] = z.w;
+    HPair* d_pairs = nullptr;
+    double* d_w = nullptr;
+    double2* acc = nullptr;
+    auto cleanup = [&]() {
+        if (d_pairs) cudaFree(d_pairs);
+        if (d_w) cudaFree(d_w);
+        if (acc) cudaFree(acc);
+    };
+    cudaError_t e = cudaMalloc(&acc, h->bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, XYK_ERR_NOMEM, "xyk_exact_step: no device memory for the accumulator (three state vectors are needed)");
+    }
+    bool ok = cudaMalloc(&d_pairs, sizeof(HPair) * std::max<size_t>(1, hp.size())) == cudaSuccess &&
+              cudaMalloc(&d_w, sizeof(double) * h->n) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(d_pairs, hp.data(), sizeof(HPair) * hp.size(), cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(d_w, wbit.data(), sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(h->stream) == cudaSuccess;
+    if (!ok) {
+        cleanup();
+        return fail(h, XYK_ERR_CUDA, std::string("xyk_exact_step: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+    const uint64_t dim = 1ull << h->nlocal;
+    const int grid = grid_for(h, dim, 256);
+    const size_t smem = sizeof(HPair) * hp.size() + sizeof(double) * h->n;
+    double2* X = (double2*)h->buf[h->cur];       // phi_{k-1}, overwritten by phi_{k+1}
+    double2* Y = (double2*)h->buf[h->cur ^ 1];   // phi_k
+    const int np = (int)hp.size();
+    // phi_1 = H phi_0 / E;  acc = c_0 phi_0 + c_1 phi_1
+    cheb_step_kernel<<<grid, 256, smem, h->stream>>>(X, nullptr, Y, acc, d_pairs, np, d_w, h->n, dim, 1.0 / E, coef(1), coef(0), 1);
+    h->stats.kernel_launches++;
+    h->stats.state_sweeps++;
+    for (int k = 1; k + 1 < nterms; ++k) {
+        // phi_{k+1} = 2 H phi_k / E - phi_{k-1}  (written over phi_{k-1});  acc += c_{k+1} phi_{k+1}
+        cheb_step_kernel<<<grid, 256, smem, h->stream>>>(Y, X, X, acc, d_pairs, np, d_w, h->n, dim, 2.0 / E, coef(k + 1), make_double2(0, 0), 0);
+        std::swap(X, Y);
+        h->stats.kernel_launches++;
+        h->stats.state_sweeps++;
+    }
+    e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(h, XYK_ERR_CUDA, std::string("xyk_exact_step: ") + cudaGetErrorString(e));
+    }
+    // the accumulator becomes the live state (layout unchanged)
+    void* old_state = h->buf[h->cur];
+    h->buf[h->cur] = acc;
+    acc = reinterpret_cast<double2*>(old_state);
+    cleanup();
+    if (terms_used) *terms_used = nterms;
     return XYK_OK;
 }
 

@@ -169,6 +169,170 @@ __global__ void pair_gate_kernel(typename cplx<real>::type* __restrict__ psi, in
     }
 }
 
+// ---- XXZ anisotropy: diagonal ZZ phases (bridge/knm_hamiltonian.py:196-201, term -K_ij delta Z_i Z_j) ----
+// psi_k *= exp(+i theta z_i z_j), z = 1 - 2 bit: one pair, gate-by-gate engine (reference term order XX, YY, ZZ per pair)
+template <typename real>
+__global__ void zz_gate_kernel(typename cplx<real>::type* __restrict__ psi, int nlocal, int pi, int pj, double c, double s) {
+    const uint64_t dim = 1ull << nlocal;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (uint64_t)gridDim.x * blockDim.x) {
+        const double sg = (((k >> pi) ^ (k >> pj)) & 1) ? -s : s;
+        typename cplx<real>::type v = psi[k];
+        const double xr = (double)v.x, xi = (double)v.y;
+        v.x = (real)(xr * c - xi * sg);
+        v.y = (real)(xr * sg + xi * c);
+        psi[k] = v;
+    }
+}
+
+// All ZZ terms at once: psi_k *= exp(+i t sum_{a<b} J[la][lb] z_a z_b) over PHYSICAL bits a, b (la = log_of_bit[a]: the
+// logical qubit on bit a; bits >= nlocal are fixed by the rank).  The bits split into Lo = [0, LB) and Hi = the rest:
+//   theta(k) = Q_lo(k_lo) + Q_hi(k_hi) + sum_{a in Lo} z_a f_a(k_hi),   f_a = sum_{b in Hi} J_ab z_b
+// Q_lo comes from a 2^LB-entry table (zz_low_table_kernel); a CTA takes one k_hi at a time, computes f_a and Q_hi, turns
+// the linear part into two 64-entry factor tables in shared memory and multiplies its 2^LB amplitudes: one read and one
+// write of the state, no trigonometry per amplitude.
+struct ZZSpec {
+    int nbits, nlocal, rank, LB;
+    int log_of_bit[kMaxQ];
+    double t;
+};
+
+__global__ void zz_low_table_kernel(double2* __restrict__ tab, const double* __restrict__ J, int ldJ, const __grid_constant__ ZZSpec S) {
+    const int cnt = 1 << S.LB;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < cnt; v += gridDim.x * blockDim.x) {
+        double q = 0.0;
+        for (int a = 0; a < S.LB; ++a)
+            for (int b = a + 1; b < S.LB; ++b) {
+                const double jab = J[S.log_of_bit[a] * ldJ + S.log_of_bit[b]];
+                q += (((v >> a) ^ (v >> b)) & 1) ? -jab : jab;
+            }
+        double sn, cs;
+        sincos(S.t * q, &sn, &cs);
+        tab[v] = make_double2(cs, sn);
+    }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) zz_diag_kernel(typename cplx<real>::type* __restrict__ psi, const double2* __restrict__ tab,
+                                                      const double* __restrict__ J, int ldJ, const __grid_constant__ ZZSpec S) {
+    __shared__ double f[16];
+    __shared__ double qhi;
+    __shared__ double2 fa[64], fb[64];
+    const int LB = S.LB, nhi = S.nbits - LB;
+    const uint64_t nblk = 1ull << (S.nlocal - LB);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t kh = blockIdx.x; kh < nblk; kh += gridDim.x) {
+        const uint64_t hibits = kh | ((uint64_t)S.rank << (S.nlocal - LB));  // bit (b - LB) of hibits = physical bit b
+        if (warp == 0) {
+            if (lane < LB) {
+                double acc = 0.0;
+                for (int b = 0; b < nhi; ++b) {
+                    const double jab = J[S.log_of_bit[lane] * ldJ + S.log_of_bit[LB + b]];
+                    acc += ((hibits >> b) & 1) ? -jab : jab;
+                }
+                f[lane] = acc;
+            }
+        } else if (warp == 1) {
+            double acc = 0.0;
+            for (int idx = lane; idx < nhi * nhi; idx += 32) {
+                const int a = idx / nhi, b = idx - a * nhi;
+                if (a < b) {
+                    const double jab = J[S.log_of_bit[LB + a] * ldJ + S.log_of_bit[LB + b]];
+                    acc += (((hibits >> a) ^ (hibits >> b)) & 1) ? -jab : jab;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) qhi = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int v = threadIdx.x & 63, half = threadIdx.x >> 6;  // half 0: bits [0, 6), half 1: bits [6, 12) (+ Q_hi)
+            double ph = half ? qhi : 0.0;
+            for (int b = 0; b < 6; ++b) {
+                const int a = half * 6 + b;
+                if (a < LB) ph += ((v >> b) & 1) ? -f[a] : f[a];
+            }
+            double sn, cs;
+            sincos(S.t * ph, &sn, &cs);
+            (half ? fb : fa)[v] = make_double2(cs, sn);
+        }
+        __syncthreads();
+        typename cplx<real>::type* base = psi + (kh << LB);
+        for (int x = threadIdx.x; x < (1 << LB); x += 256) {
+            const double2 t0 = __ldg(&tab[x]), t1 = fa[x & 63], t2 = fb[x >> 6];
+            const double ar = t0.x * t1.x - t0.y * t1.y, ai = t0.x * t1.y + t0.y * t1.x;
+            const double fr = ar * t2.x - ai * t2.y, fi = ar * t2.y + ai * t2.x;
+            typename cplx<real>::type v = base[x];
+            const double xr = (double)v.x, xi = (double)v.y;
+            v.x = (real)(xr * fr - xi * fi);
+            v.y = (real)(xr * fi + xi * fr);
+            base[x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- exact step by Chebyshev expansion on a fused H.phi sweep (reference twin: hardware/classical.py:201-208, expm_multiply) ----
+// H = -sum_{i<j} K_ij (XX + YY + delta ZZ) - sum_i w_i Z_i acts on amplitude k as
+//   (H phi)_k = d(k) phi_k - 2 sum_{(a,b): bits differ} K_ab phi_{k ^ (m_a | m_b)},   d(k) = -sum_a w_a z_a - delta sum K_ab z_a z_b
+// (scpn_quantum_engine/src/hamiltonian.rs:55-78).  The pair terms are SUMMED, so there is no ordering constraint: one
+// kernel applies all of them.  A warp's 32 consecutive k gather 32 consecutive (or lane-permuted) amplitudes per pair:
+// every gather is one coalesced 512-byte read that the L2 serves while the state fits it.
+struct HPair {
+    unsigned long long ma, mb;  // bit masks of the two qubits in the current layout
+    double k, kz;               // K_ab and K_ab * delta
+};
+
+// next = alpha (H cur) / E - prev (prev == nullptr: no subtraction);  acc = (first ? 0 : acc) ... see flags:
+//   acc_mode 0: acc += coef * next;  1: acc = coef0 * cur + coef * next (first term of the series)
+__global__ void __launch_bounds__(256) cheb_step_kernel(const double2* __restrict__ cur, const double2* prev, double2* next,
+                                                        double2* __restrict__ acc, const HPair* __restrict__ pairs, int npairs,
+                                                        const double* __restrict__ wbit, int nbits, uint64_t dim, double alpha_over_E,
+                                                        double2 coef, double2 coef0, int acc_mode) {
+    extern __shared__ unsigned char cheb_smem[];
+    HPair* sp = reinterpret_cast<HPair*>(cheb_smem);
+    double* sw = reinterpret_cast<double*>(sp + npairs);
+    for (int t = threadIdx.x; t < npairs; t += blockDim.x) sp[t] = pairs[t];
+    for (int t = threadIdx.x; t < nbits; t += blockDim.x) sw[t] = wbit[t];
+    __syncthreads();
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (uint64_t)gridDim.x * blockDim.x) {
+        double diag = 0.0;
+        for (int b = 0; b < nbits; ++b) diag += ((k >> b) & 1) ? sw[b] : -sw[b];
+        double hr = 0.0, hi = 0.0;
+        for (int t = 0; t < npairs; ++t) {
+            const HPair pr = sp[t];
+            const bool differ = ((k & pr.ma) != 0) != ((k & pr.mb) != 0);
+            if (differ) {
+                const double2 v = __ldg(&cur[k ^ (pr.ma | pr.mb)]);
+                hr -= 2.0 * pr.k * v.x;
+                hi -= 2.0 * pr.k * v.y;
+                diag += pr.kz;
+            } else {
+                diag -= pr.kz;
+            }
+        }
+        const double2 c = cur[k];
+        hr += diag * c.x;
+        hi += diag * c.y;
+        double nr = alpha_over_E * hr, ni = alpha_over_E * hi;
+        if (prev) {
+            const double2 p = prev[k];
+            nr -= p.x;
+            ni -= p.y;
+        }
+        next[k] = make_double2(nr, ni);
+        double ar = coef.x * nr - coef.y * ni, ai = coef.x * ni + coef.y * nr;
+        if (acc_mode == 1) {
+            ar += coef0.x * c.x - coef0.y * c.y;
+            ai += coef0.x * c.y + coef0.y * c.x;
+        } else {
+            const double2 a = acc[k];
+            ar += a.x;
+            ai += a.y;
+        }
+        acc[k] = make_double2(ar, ai);
+    }
+}
+
 // (a, b) = (psi[..0_pos..], psi[..1_pos..]) <- (c a - s b, s a + c b): Ry(theta) with c = cos(theta/2), s = sin(theta/2)
 template <typename real>
 __global__ void ry_gate_kernel(typename cplx<real>::type* __restrict__ psi, int nlocal, int pos, double c, double s) {

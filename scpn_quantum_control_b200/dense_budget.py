@@ -96,3 +96,19 @@ def require_statevector_allocation(
             f"backend instead of dense allocation."
         )
     return est
+
+
+def statevector_qubit_budget(*, itemsize: int = 16, buffers: int = 2, device: int = 0, max_gib: float | None = None) -> int:
+    """Largest n whose ``buffers`` state copies fit the active per-device budget (the GPU analogue of the reference's
+    fixed ``MAX_STATEVECTOR_OSCILLATORS = 16``, benchmarks/reproducible_comparison.py:51)."""
+    from .engine import device_memory
+
+    try:
+        free, _total = device_memory(device)
+    except RuntimeError:
+        free = None
+    budget = budget_bytes(max_gib, free)
+    n = 1
+    while (1 << (n + 1)) * itemsize * buffers <= budget:
+        n += 1
+    return n

@@ -80,12 +80,16 @@ class XYKEngine:
         table = {"auto": _lib.ENGINE_AUTO, "simple": _lib.ENGINE_SIMPLE, "tiled": _lib.ENGINE_TILED}
         self.set_option(_lib.OPT_ENGINE, table[name])
 
-    def set_problem(self, K: np.ndarray, omega: np.ndarray) -> None:
+    def set_problem(self, K: np.ndarray, omega: np.ndarray, delta: float = 0.0) -> None:
+        """(K, omega) of the XY model; ``delta`` != 0: XXZ anisotropy (knm_to_xxz_hamiltonian)."""
         K = np.ascontiguousarray(K, dtype=np.float64)
         omega = np.ascontiguousarray(omega, dtype=np.float64)
         if K.shape != (self.n, self.n) or omega.shape != (self.n,):
             raise ValueError("K must be (n, n) and omega (n,)")
-        self._check(self._lib.xyk_set_problem(self._h, _dptr(K), _dptr(omega)))
+        if delta == 0.0:
+            self._check(self._lib.xyk_set_problem(self._h, _dptr(K), _dptr(omega)))
+        else:
+            self._check(self._lib.xyk_set_problem_xxz(self._h, _dptr(K), _dptr(omega), float(delta)))
 
     def term_counts(self) -> tuple[int, int]:
         a, b = c_int(), c_int()
@@ -94,6 +98,19 @@ class XYKEngine:
 
     def init_product_state(self) -> None:
         self._check(self._lib.xyk_init_product_state(self._h))
+
+    def exact_step(self, dt: float, tol: float = 1e-13) -> int:
+        """psi <- exp(-i H dt) psi by Chebyshev expansion (no splitting error); returns the number of terms."""
+        used = c_int()
+        self._check(self._lib.xyk_exact_step(self._h, float(dt), float(tol), byref(used)))
+        return used.value
+
+    def init_product_angles(self, angles: np.ndarray) -> None:
+        """|psi> = prod_q Ry(angles[q])|0> (0: |0...0>, pi/2: |+>^n)."""
+        a = np.ascontiguousarray(angles, dtype=np.float64)
+        if a.shape != (self.n,):
+            raise ValueError(f"angles must have shape ({self.n},), got {a.shape}")
+        self._check(self._lib.xyk_init_product_angles(self._h, _dptr(a)))
 
     def apply_layers(self, delta: float, order: int = 1, reps: int = 1) -> int:
         return self._check(self._lib.xyk_apply_layers(self._h, float(delta), int(order), int(reps)))

@@ -138,8 +138,13 @@ class QuantumKuramotoSolver:
         device: int = 0,
         exact_tol: float = 2e-10,
         distributed: bool = False,
+        anisotropy_delta: float = 0.0,
     ):
-        """K_coupling: (n,n) coupling matrix, omega_natural: (n,) frequencies."""
+        """K_coupling: (n,n) coupling matrix, omega_natural: (n,) frequencies.
+
+        ``anisotropy_delta`` != 0 evolves the XXZ Hamiltonian of ``knm_to_xxz_hamiltonian(K, omega, delta)``
+        (reference bridge/knm_hamiltonian.py:141-206) instead of the XY model; ``evolution="trotter"`` then runs gate by
+        gate in the reference's term order (XX, YY, ZZ per pair), ``evolution="reference"`` through the tiled engine."""
         self.n = self._validate_n_oscillators(n_oscillators)
         self.K = _as_real_numeric_array("K_coupling", K_coupling)
         self.omega = _as_real_numeric_array("omega_natural", omega_natural)
@@ -151,8 +156,10 @@ class QuantumKuramotoSolver:
             raise ValueError(f"trotter_order must be 1 or 2, got {order}")
         self.evolution_config = replace(config, order=order)
         self.trotter_order = self.evolution_config.order
-        if evolution not in ("reference", "trotter"):
-            raise ValueError(f"evolution must be 'reference' or 'trotter', got {evolution!r}")
+        if evolution not in ("reference", "trotter", "chebyshev"):
+            raise ValueError(f"evolution must be 'reference', 'trotter' or 'chebyshev', got {evolution!r}")
+        if evolution == "chebyshev" and (dtype != "complex128" or distributed):
+            raise ValueError("evolution='chebyshev' needs a single-device complex128 state")
         if dtype not in ("complex128", "complex64"):
             raise ValueError(f"dtype must be 'complex128' or 'complex64', got {dtype!r}")
         self.evolution = evolution
@@ -164,6 +171,11 @@ class QuantumKuramotoSolver:
         self.distributed = bool(distributed)
         if self.distributed and dtype != "complex128":
             raise ValueError("distributed=True supports dtype='complex128' only (sharded states are complex128)")
+        if not np.isfinite(anisotropy_delta):
+            raise ValueError(f"anisotropy_delta must be finite, got {anisotropy_delta}")
+        self.anisotropy_delta = float(anisotropy_delta) if abs(anisotropy_delta) > 1e-15 else 0.0
+        if self.anisotropy_delta and self.distributed:
+            raise ValueError("anisotropy_delta != 0 is not supported with distributed=True")
         self._engine = None
         self._exact_reps_cache: dict[tuple[float, float], int] = {}
         self._calibrate_direct_max_n = _CALIBRATE_DIRECT_MAX_N
@@ -221,9 +233,17 @@ class QuantumKuramotoSolver:
                 eng = ShardedXYKEngine(self.n, device=self.device)
             else:
                 eng = XYKEngine(self.n, dtype=self.dtype, device=self.device)
-            eng.set_problem(self.K, self.omega)
+            self._set_problem_on(eng, self.K, self.omega)
             self._engine = eng
         return self._engine
+
+    def _set_problem_on(self, eng, K, omega) -> None:
+        if self.anisotropy_delta:
+            eng.set_problem(K, omega, self.anisotropy_delta)
+            if self.evolution == "trotter":
+                eng.set_engine("gates")  # the literal product formula in the reference's term order: XX, YY, ZZ per pair
+        else:
+            eng.set_problem(K, omega)
 
     def update_problem(self, K_coupling, omega_natural=None) -> None:
         """Re-parameterise (K, omega) on the live engine: same validation as the constructor, the
@@ -236,7 +256,7 @@ class QuantumKuramotoSolver:
         self.K, self.omega = K, omega
         self._exact_reps_cache.clear()
         if self._engine is not None:
-            self._engine.set_problem(self.K, self.omega)
+            self._set_problem_on(self._engine, self.K, self.omega)
 
     def close(self) -> None:
         if self._engine is not None:
@@ -287,7 +307,7 @@ class QuantumKuramotoSolver:
             self.exact_calibration = {"kind": "reduced_problem", "n": n_cal, "safety_factor": safety}
         eng = XYKEngine(n_cal, dtype=self.dtype, device=self.device)
         try:
-            eng.set_problem(K_cal, w_cal)
+            self._set_problem_on(eng, K_cal, w_cal)
 
             def observe(reps: int) -> np.ndarray:
                 eng.init_product_state()
@@ -310,12 +330,20 @@ class QuantumKuramotoSolver:
         trotter_steps = self.evolution_config.evolve_steps if trotter_steps is None else trotter_steps
         if not isinstance(trotter_steps, int) or trotter_steps < 1:
             raise ValueError(f"trotter_steps must be a positive integer, got {trotter_steps}")
+        if self.evolution == "chebyshev":
+            self.engine().exact_step(float(time), self.exact_tol * 1e-3)
+            return
         order, reps = self._formula(float(time), trotter_steps)
         self.engine().apply_layers(float(time), order, reps)
 
     def prepare_initial_state(self) -> None:
         """|psi0> = prod_i Ry(omega_i mod 2pi)|0> on the device (reference :236-242)."""
         self.engine().init_product_state()
+
+    def prepare_product_state(self, angles) -> None:
+        """|psi> = prod_i Ry(angles_i)|0> on the device: zeros give |0...0> (``Statevector.from_label("0" * n)``,
+        reference scripts/bench_s2_scaling_lite.py:262), pi/2 gives |+>^n (phase/floquet_kuramoto.py:131)."""
+        self.engine().init_product_angles(np.asarray(angles, dtype=np.float64))
 
     def measure_order_parameter(self, sv=None) -> tuple[float, float]:
         """R exp(i psi) = (1/N) sum_j (<X_j> + i <Y_j>) of the live state (reference :156-185).
@@ -376,7 +404,17 @@ class QuantumKuramotoSolver:
             for s in np.unique(np.round(step_sizes, 15)):
                 exact_reps[float(s)] = self._calibrated_exact_reps(float(s), len(step_sizes))
 
-        if self.n <= _SMALL_N and self.dtype == "complex128" and not self.distributed:
+        if self.evolution == "chebyshev":
+            # exact step without a product formula: Chebyshev expansion on the fused H.phi sweep (xyk_exact_step)
+            eng = self.engine()
+            eng.init_product_state()
+            R_history = np.zeros(times.shape[0])
+            R_history[0], _ = eng.order_parameter()
+            cheb_terms = []
+            for step, step_dt in enumerate(step_sizes, start=1):
+                cheb_terms.append(eng.exact_step(float(step_dt), self.exact_tol * 1e-3))
+                R_history[step], _ = eng.order_parameter()
+        elif self.n <= _SMALL_N and self.dtype == "complex128" and not self.distributed and not self.anisotropy_delta:
             R_history = self._run_small(step_sizes, trotter_per_step, exact_reps)
         elif not self.distributed and self._uniform_formula(step_sizes, trotter_per_step) is not None:
             # one C call enqueues the whole trajectory (state preparation, layers, R(t) on the device, one read-back)
@@ -399,6 +437,8 @@ class QuantumKuramotoSolver:
             "evolution": self.evolution,
             "dtype": self.dtype,
         }
+        if self.evolution == "chebyshev":
+            meta["chebyshev_terms_per_step"] = cheb_terms
         if self.evolution == "reference":
             meta["exact_composition"] = {"order": 6, "reps": {str(k): v for k, v in exact_reps.items()},
                                          "calibration": self.exact_calibration}

@@ -66,3 +66,211 @@ def test_feedback_controller_history_vs_oracle(n, evolution, order):
     assert ctl.coupling_scale == 1.0 and not ctl.history
     assert 1.0 - oc.fidelity(ctl.statevector, oc.initial_state(w)) < FID_TOL
     ctl.close()
+
+
+def test_product_angle_states():
+    """xyk_init_product_angles: |0...0>, |+>^n and a general Ry product state"""
+    n = 13
+    rng = np.random.default_rng(3)
+    for ang in (np.zeros(n), np.full(n, np.pi / 2), rng.uniform(0, 2 * np.pi, n)):
+        with XYKEngine(n) as eng:
+            eng.init_product_angles(ang)
+            got = eng.get_state()
+        want = np.ones(1, dtype=np.complex128)
+        for q in range(n):
+            want = np.kron(np.array([np.cos(ang[q] / 2), np.sin(ang[q] / 2)]), want)
+        assert np.abs(got - want).max() < 1e-14
+
+
+def test_benchmark_callers_vs_oracle():
+    """the four swap-in call sites of SURVEY 8(f) row 3, on the GPU solver, against the oracle"""
+    from scpn_quantum_control_b200 import benchmarks as bm
+
+    n = 10
+    K, w = oc.paper27_K(n), oc.OMEGA_N_16[:n]
+    out = bm.quantum_benchmark(n, t_max=0.3, dt=0.1, trotter_reps=2)
+    assert out["n_trotter_steps"] == 6 and out["t_total_ms"] > 0.0
+    _, RE = oc.run(n, K, w, 0.3, 0.1, mode="E")
+    row = bm.quantum_trotter_row(n, 0.3, 0.1, 5, r_exact=RE[-1])
+    assert row.available and row.method == "quantum_trotter" and row.r_error_vs_exact < R_TOL
+    assert set(row.to_dict()) == {"method", "backend", "available", "r_final", "r_error_vs_exact", "elapsed_ms",
+                                  "unavailable_reason"}
+    _, RT = oc.run(n, K, w, 0.3, 0.1, 5, order=1, mode="T")
+    rowT = bm.quantum_trotter_row(n, 0.3, 0.1, 5, evolution="trotter")
+    assert abs(rowT.r_final - RT[-1]) < R_TOL
+    spec = {"K_nm": K.tolist(), "omega": w.tolist(), "t_max": 0.3, "dt": 0.1, "trotter_per_step": 5, "trotter_order": 1}
+    sim = bm.simulate_execute(spec)
+    assert sim["n_time_points"] == 4 and np.abs(np.array(sim["R"]) - RE).max() < R_TOL
+    assert sim["R_final"] == sim["R"][-1] and sim["n_nodes"] == n
+    # |0...0> is an eigenstate of every XX+YY term and of Z: R stays 0 exactly, in any mode
+    srow = bm.statevector_scaling_row(14)
+    assert srow["status"] == "ok" and abs(srow["metric_payload"]["final_R"]) < 1e-12
+    assert bm.statevector_scaling_row(14, max_statevector_qubits=12)["status"] == "skipped"
+
+
+def test_scaling_row_state_vs_oracle():
+    """evolve(0.1, 1) from |0...0> with a superposed start instead: Ry(pi/3) product state through the same calls"""
+    from scpn_quantum_control_b200 import QuantumKuramotoSolver
+
+    n = 14
+    K = oc.paper27_K(n)
+    w = oc.OMEGA_N_16[:n]
+    ang = np.full(n, np.pi / 3)
+    s = QuantumKuramotoSolver(n, K, w, evolution="trotter")
+    s.prepare_product_state(ang)
+    s.evolve(0.1, trotter_steps=1)
+    R, psi_ang = s.measure_order_parameter()
+    got = s.statevector()
+    s.close()
+    psi = np.ones(1, dtype=np.complex128)
+    for q in range(n):
+        psi = np.kron(np.array([np.cos(ang[q] / 2), np.sin(ang[q] / 2)]), psi)
+    Kc, wc = oc.canonicalise(n, K, w)
+    z, p = oc.term_list(Kc, wc)
+    psi = oc.evolve_product_formula(psi.astype(np.complex128), z, p, 0.1, 1, 1)
+    assert 1.0 - oc.fidelity(got, psi) < FID_TOL
+    assert abs(R - oc.order_parameter(psi, n)[0]) < R_TOL
+
+
+@pytest.mark.parametrize("n,order", [(5, 1), (9, 2), (13, 1), (13, 2)])
+def test_xxz_gate_by_gate_in_reference_term_order(n, order):
+    """delta != 0, literal product formula: XX.YY then ZZ per pair (bridge/knm_hamiltonian.py:176-201) vs the oracle"""
+    K, w = oc.random_problem(n, 900 + n)
+    Kc, wc = oc.canonicalise(n, K, w)
+    delta, dt, reps = 0.7, 0.1, 2
+    with XYKEngine(n) as eng:
+        eng.set_problem(Kc, wc, delta)
+        eng.set_engine("gates")
+        eng.init_product_state()
+        eng.apply_layers(dt, order, reps)
+        got = eng.get_state()
+        R, _ = eng.order_parameter()
+    z, p = on.term_list_xxz(Kc, wc, delta)
+    psi = oc.initial_state(wc)
+    for _ in range(reps):
+        psi = (on.layer_order1_xxz if order == 1 else on.layer_order2_xxz)(psi, n, z, p, dt / reps)
+    assert 1.0 - oc.fidelity(got, psi) < FID_TOL
+    assert np.abs(got - psi).max() < 1e-9  # the global phase of the ZZ terms is kept
+    assert abs(R - oc.order_parameter(psi, n)[0]) < R_TOL
+
+
+@pytest.mark.parametrize("n", [13, 16, 18])
+def test_xxz_tiled_grouped_diagonal_vs_oracle(n):
+    """delta != 0 through the fused tile passes: the ZZ terms ride with the diagonal phase (one extra sweep per half
+    layer, zz_diag_kernel) -- against the oracle's restatement of exactly that splitting"""
+    K, w = oc.random_problem(n, 950 + n)
+    Kc, wc = oc.canonicalise(n, K, w)
+    delta, dt, reps = -0.45, 0.08, 2
+    with XYKEngine(n) as eng:
+        eng.set_problem(Kc, wc, delta)
+        eng.set_engine("tiled")
+        eng.init_product_state()
+        eng.apply_layers(dt, 2, reps)
+        got = eng.get_state()
+        st = eng.stats()
+    assert st["pass_launches"] > 0
+    z, p = on.term_list_xxz(Kc, wc, delta)
+    psi = oc.initial_state(wc)
+    for _ in range(reps):
+        psi = on.layer_order2_xxz_grouped(psi, n, z, p, dt / reps)
+    assert 1.0 - oc.fidelity(got, psi) < FID_TOL
+    assert np.abs(got - psi).max() < 1e-9
+
+
+@pytest.mark.parametrize("n", [6, 13])
+def test_xxz_solver_reference_mode_vs_exact(n):
+    """QuantumKuramotoSolver(anisotropy_delta=...) in its default (exact per step) mode vs expm_multiply of the XXZ H"""
+    from scpn_quantum_control_b200 import QuantumKuramotoSolver
+
+    K = oc.paper27_K(16)[:n, :n]
+    w = oc.OMEGA_N_16[:n]
+    s = QuantumKuramotoSolver(n, K, w, anisotropy_delta=1.0)
+    res = s.run(0.3, 0.1)
+    s.close()
+    _, RE = on.run_xxz(n, K, w, 1.0, 0.3, 0.1, mode="E")
+    assert np.abs(res["R"] - RE).max() < R_TOL
+    st = QuantumKuramotoSolver(n, K, w, anisotropy_delta=1.0, evolution="trotter", trotter_order=2)
+    rt = st.run(0.3, 0.1, 3)
+    st.close()
+    _, RT = on.run_xxz(n, K, w, 1.0, 0.3, 0.1, 3, order=2, mode="T")
+    assert np.abs(rt["R"] - RT).max() < R_TOL
+
+
+@pytest.mark.parametrize("n", [4, 8, 13])
+def test_floquet_evolve_vs_oracle(n):
+    """floquet_evolve (phase/floquet_kuramoto.py:94-182) on the device vs the oracle's exact midpoint propagation"""
+    from scpn_quantum_control_b200.floquet_kuramoto import floquet_evolve, scan_drive_amplitude
+
+    K = oc.paper27_K(16)[:n, :n]
+    top = K / K.max()
+    w = oc.OMEGA_N_16[:n]
+    periods, spp = (2, 8) if n < 13 else (1, 4)
+    got = floquet_evolve(top, w, 0.5, 0.6, 2.0, periods, spp)
+    want = on.floquet_evolve(top, w, 0.5, 0.6, 2.0, periods, spp)
+    assert np.allclose(got.times, want["times"], rtol=0, atol=1e-14)
+    assert np.allclose(got.drive_signal, want["drive_signal"], rtol=0, atol=1e-14)
+    # the phase-coherence R divides by |<X>+i<Y>| per qubit: a little less well conditioned than the solver's R
+    assert np.abs(got.R_values - want["R_values"]).max() < 1e-8
+    assert got.subharmonic_ratio == pytest.approx(want["subharmonic_ratio"], rel=1e-6, abs=1e-9)
+    assert got.is_dtc_candidate == (want["subharmonic_ratio"] > 0.1)
+    if n == 4:
+        sc = scan_drive_amplitude(top, w, 0.5, 2.0, amplitudes=[0.2, 1.0], n_periods=2, steps_per_period=8)
+        assert sc["amplitude"] == [0.2, 1.0] and len(sc["mean_R"]) == 2
+        ref = on.floquet_evolve(top, w, 0.5, 1.0, 2.0, 2, 8)
+        assert sc["subharmonic_ratio"][1] == pytest.approx(ref["subharmonic_ratio"], rel=1e-6, abs=1e-9)
+
+
+@pytest.mark.parametrize("n,delta,dt", [(4, 0.0, 0.1), (9, 0.0, 0.3), (14, 0.0, 0.1), (10, 0.8, 0.2), (14, 0.0, -0.15)])
+def test_chebyshev_exact_step_vs_expm_multiply(n, delta, dt):
+    """xyk_exact_step (Chebyshev series on the fused H.phi sweep) vs scipy's expm_multiply of the oracle's sparse H --
+    the reference twin hardware/classical.py:201-208 -- after a tiled evolution (permuted layout)"""
+    K, w = oc.random_problem(n, 300 + n)
+    Kc, wc = oc.canonicalise(n, K, w)
+    with XYKEngine(n) as eng:
+        eng.set_problem(Kc, wc, delta)
+        eng.init_product_state()
+        if n >= 13 and delta == 0.0:
+            eng.set_engine("tiled")
+            eng.apply_layers(0.05, 2, 1)  # leaves a permuted layout behind
+        terms = eng.exact_step(dt, 1e-14)
+        got = eng.get_state()
+        R, _ = eng.order_parameter()
+    psi = oc.initial_state(wc)
+    if n >= 13 and delta == 0.0:
+        z, p = oc.term_list(Kc, wc)
+        psi = oc.evolve_product_formula(psi, z, p, 0.05, 1, 2)
+    psi = oc.exact_step(psi, on.hamiltonian_sparse_xxz(Kc, wc, delta), dt)
+    assert terms > 3
+    assert 1.0 - oc.fidelity(got, psi) < FID_TOL
+    assert np.abs(got - psi).max() < 1e-10
+    assert abs(R - oc.order_parameter(psi, n)[0]) < R_TOL
+
+
+def test_chebyshev_solver_vs_goldens_and_composition():
+    """evolution="chebyshev" reproduces the reference's stored n=8 run (Mode E) and agrees with the calibrated
+    6th-order composition at n=18 where no CPU oracle is cheap"""
+    import json
+    import os
+
+    from scpn_quantum_control_b200 import QuantumKuramotoSolver
+
+    n = 8
+    K, w = oc.paper27_K(n), oc.OMEGA_N_16[:n]
+    s = QuantumKuramotoSolver(n, K, w, evolution="chebyshev")
+    res = s.run(1.0, 0.1)
+    s.close()
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")))
+    _, RE = oc.run(n, K, w, 1.0, 0.1, mode="E")
+    assert np.abs(res["R"] - RE).max() < R_TOL
+    assert "chebyshev_terms_per_step" in res.metadata
+    flat = json.dumps(gold)
+    assert "0.25916072998431" in flat and abs(res["R"][-1] - 0.259160729984313) < R_TOL  # reproducible_comparison_n8.json r_final
+    n = 18
+    K, w = oc.random_problem(n, 77)
+    a = QuantumKuramotoSolver(n, K, w, evolution="chebyshev")
+    ra = a.run(0.2, 0.1)
+    a.close()
+    b = QuantumKuramotoSolver(n, K, w)
+    rb = b.run(0.2, 0.1)
+    b.close()
+    assert np.abs(ra["R"] - rb["R"]).max() < R_TOL
