@@ -241,7 +241,7 @@ class QuantumKuramotoSolver:
         if self.anisotropy_delta:
             eng.set_problem(K, omega, self.anisotropy_delta)
             if self.evolution == "trotter":
-                eng.set_engine("gates")  # the literal product formula in the reference's term order: XX, YY, ZZ per pair
+                eng.set_engine("simple")  # the literal product formula in the reference's term order: XX, YY, ZZ per pair
         else:
             eng.set_problem(K, omega)
 
