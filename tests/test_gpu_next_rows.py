@@ -274,3 +274,51 @@ def test_chebyshev_solver_vs_goldens_and_composition():
     rb = b.run(0.2, 0.1)
     b.close()
     assert np.abs(ra["R"] - rb["R"]).max() < R_TOL
+
+
+C64_FID_TOL = 1e-5   # stated bound of the complex64 variant: fidelity >= 1 - 1e-5,
+C64_R_TOL = 1e-4     # |dR| <= 1e-4 for runs of <= 25 000 gates; coefficients and reductions stay double
+
+
+@pytest.mark.parametrize("n,reps", [(14, 4), (20, 2), (24, 1)])
+def test_complex64_state_within_stated_bound(n, reps):
+    """complex64 state (8 B per amplitude, gate-by-gate kernels, FP64 coefficients / accumulation) vs the FP64 C oracle"""
+    import ctypes
+    import os
+
+    K, w = oc.random_problem(n, 640 + n)
+    Kc, wc = oc.canonicalise(n, K, w)
+    with XYKEngine(n, dtype="complex64") as eng:
+        eng.set_problem(Kc, wc)
+        eng.init_product_state()
+        eng.apply_layers(0.1, 1, reps)
+        R, _ = eng.order_parameter()
+        ex, ey = eng.xy_expectations()
+        got = eng.get_state()
+        nrm = eng.norm2()
+    assert got.dtype == np.complex64
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_build", "libxyoracle.so")
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    psi = np.zeros(2 << n)
+    lib.xyo_init_state(n, wc.ctypes.data_as(dp), psi.ctypes.data_as(dp))
+    lib.xyo_evolve.argtypes = [ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_int, dp]
+    lib.xyo_evolve(n, np.ascontiguousarray(Kc).ctypes.data_as(dp), wc.ctypes.data_as(dp), 0.1, reps, 1, psi.ctypes.data_as(dp))
+    ref = psi.view(np.complex128)
+    assert 1.0 - oc.fidelity(got.astype(np.complex128), ref) < C64_FID_TOL
+    Rref, _ = oc.order_parameter(ref, n)
+    assert abs(R - Rref) < C64_R_TOL
+    assert abs(nrm - 1.0) < 1e-4
+
+
+def test_complex64_solver_run():
+    from scpn_quantum_control_b200 import QuantumKuramotoSolver
+
+    n = 14
+    K, w = oc.random_problem(n, 655)
+    s = QuantumKuramotoSolver(n, K, w, dtype="complex64", evolution="trotter")
+    res = s.run(0.4, 0.1, 3)
+    s.close()
+    _, RT = oc.run(n, K, w, 0.4, 0.1, 3, order=1, mode="T")
+    assert res.metadata["dtype"] == "complex64"
+    assert np.abs(res["R"] - RT).max() < C64_R_TOL
