@@ -528,7 +528,13 @@ PassKernel pass_kernel_unb(bool lift, bool peer) {
     if (lift) return peer ? tile_pass_kernel<kTB, kRB, true, kPassMinBlocks, true, UNB, kPassGroups> : tile_pass_kernel<kTB, kRB, true, kPassMinBlocks, false, UNB, kPassGroups>;
     return peer ? tile_pass_kernel<kTB, kRB, false, kPassMinBlocks, true, UNB, kPassGroups> : tile_pass_kernel<kTB, kRB, false, kPassMinBlocks, false, UNB, kPassGroups>;
 }
-PassKernel pass_kernel_fn(bool lift, bool peer, int unb) {
+// complex64 storage (8-byte amplitudes in global memory, FP64 on chip): single-device states only, so no peer variant
+template <int UNB>
+PassKernel pass_kernel_c64_unb(bool lift) {
+    return lift ? tile_pass_kernel<kTB, kRB, true, kPassMinBlocks, false, UNB, kPassGroups, true> : tile_pass_kernel<kTB, kRB, false, kPassMinBlocks, false, UNB, kPassGroups, true>;
+}
+PassKernel pass_kernel_fn(bool lift, bool peer, int unb, bool c64 = false) {
+    if (c64) return unb == 2 ? pass_kernel_c64_unb<2>(lift) : (unb == 1 ? pass_kernel_c64_unb<1>(lift) : pass_kernel_c64_unb<0>(lift));
     return unb == 2 ? pass_kernel_unb<2>(lift, peer) : (unb == 1 ? pass_kernel_unb<1>(lift, peer) : pass_kernel_unb<0>(lift, peer));
 }
 // 0: balanced rounds only; 1 / 2: the pass holds 1 | 5 / 2 | 4 split rounds (the schedule compiler never mixes the two)
@@ -546,6 +552,7 @@ int desc_unbalanced(const Desc& d) {
 int configure_pass_kernels(xyk_handle h) {
     const int smem = kPassGroups * (int)tile_bytes<kTB>();
     for (int k = 0; k < 12; ++k) XYK_CUDA(h, cudaFuncSetAttribute(pass_kernel_fn(k & 1, k & 2, k >> 2), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int k = 0; k < 6; ++k) XYK_CUDA(h, cudaFuncSetAttribute(pass_kernel_fn(k & 1, false, k >> 1, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0;
     XYK_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel_fn(true, false, 0), kPassGroups << (kTB - kRB), smem));
     if (occ < 1) occ = 1;
@@ -633,7 +640,7 @@ int run_passes(xyk_handle h, Program& prog, size_t p0, size_t p1, bool peer) {
         } else
 #endif
         {
-            pass_kernel_fn(prog.lift[p] != 0, peer, desc_unbalanced(prog.descs[p]))<<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
+            pass_kernel_fn(prog.lift[p] != 0, peer, desc_unbalanced(prog.descs[p]), h->dtype != 0)<<<grid, nthr, smem, h->stream>>>(in, out, prog.descs[p], ntiles, peers);
         }
         if (h->stats.timing_enabled) cudaEventRecord(h->pass_events[2 * p + 1], h->stream);
         h->cur ^= 1;
@@ -703,7 +710,7 @@ int run_program_tiled(xyk_handle h, Program& prog) {
 }
 
 bool use_tiled(xyk_handle h) {
-    if (h->dtype != 0) return false;  // complex64 runs gate by gate in this build
+    if (h->dtype != 0 && h->world > 1) return false;  // complex64 states are single-device
     if (h->engine_opt == XYK_ENGINE_SIMPLE) return false;
     if (h->nlocal < kTB) return false;
     if (h->nlocal > 31) return false;  // the fused store of the pass kernel indexes amplitudes with 32-bit offsets (2 * 2^31 would wrap)

@@ -661,10 +661,13 @@ struct PeerPtrs {
     double2* p[8];
 };
 
-template <bool PEER>
+template <bool PEER, bool C64 = false>
 __device__ __forceinline__ void store_out(double2* __restrict__ out, const PeerPtrs& peers, int nl, uint64_t addr,
                                           const double2& v) {
-    if constexpr (PEER) {
+    if constexpr (C64) {  // complex64 state: 8-byte amplitudes in global memory, FP64 everywhere on chip
+        static_assert(!PEER, "complex64 states are not sharded");
+        __stcs(reinterpret_cast<float2*>(out) + addr, make_float2((float)v.x, (float)v.y));
+    } else if constexpr (PEER) {
         double2* base = peers.p[addr >> nl];
         __stcs(base + (addr & ((1ull << nl) - 1ull)), v);
     } else {
@@ -731,6 +734,25 @@ __device__ __forceinline__ void bulk_load_tile(uint32_t smem_dst, const double2*
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst + sgm * (kSeg + 16u)),
                      "l"(reinterpret_cast<const char*>(gsrc) + (size_t)sgm * kSeg), "r"(kSeg), "r"(mbar)
                      : "memory");
+}
+
+// complex64 state: the tile's 2^TB float2 amplitudes (8 << TB bytes, contiguous) arrive at the FRONT of the tile buffer; the
+// group then widens them in place into the FP64 arrival layout (widen_tile_c64) before round 0 reads the tile.
+template <int TB>
+__device__ __forceinline__ void bulk_load_tile_c64(uint32_t smem_dst, const char* gsrc, uint32_t mbar) {
+    constexpr uint32_t kBytes = 8u << TB, kSeg = kBytes < 8192u ? kBytes : 8192u;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(kBytes) : "memory");
+#pragma unroll
+    for (uint32_t off = 0; off < kBytes; off += kSeg)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst + off),
+                     "l"(gsrc + off), "r"(kSeg), "r"(mbar)
+                     : "memory");
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
 }
 
 // The per-round descriptors are copied from the kernel parameter (constant bank) into shared memory
@@ -832,10 +854,24 @@ __device__ __forceinline__ void split_gates(double (&v)[NV], uint32_t mask, cons
     }
 }
 
-template <int NL, int RS, int NV, bool PEER>
+template <int NL, int RS, int NV, bool PEER, bool C64 = false>
 __device__ __forceinline__ void split_global_store(const double (&v)[NV], double2* __restrict__ out, const PeerPtrs& peers, int nq,
                                                    uint64_t dbase, const uint8_t* last_reg_out, uint32_t half, uint32_t smask) {
-    if constexpr (PEER) {
+    if constexpr (C64) {
+        static_assert(!PEER, "complex64 states are not sharded");
+        char* pb = reinterpret_cast<char*>(out) + (dbase << 3);
+        char* pb0 = pb + (half << 2);      // elements with role 0: component `half`
+        char* pb1 = pb + 4 - (half << 2);  // elements with role 1: the other component
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint64_t off = 0;
+#pragma unroll
+            for (int k = 0; k < RS; ++k)
+                if ((j >> k) & 1) off += 8ull << last_reg_out[k];
+            const bool fj = __builtin_popcount(j >> NL) & 1;
+            __stcs(reinterpret_cast<float*>((fj ? pb1 : pb0) + off), (float)(fj ? flip_sign(v[j], smask) : v[j]));
+        }
+    } else if constexpr (PEER) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             uint64_t off = 0;
@@ -1016,10 +1052,14 @@ __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads)
     asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int TB, int RB, bool LIFT, int MINB, bool PEER, int UNB, int NG>
+// C64: the state in global memory is complex64 (8 B per amplitude; `in` / `out` point to float2 data), everything on chip is FP64.
+template <int TB, int RB, bool LIFT, int MINB, bool PEER, int UNB, int NG, bool C64 = false>
 __global__ void __launch_bounds__(NG << (TB - RB), MINB)
 tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                  const __grid_constant__ PassDesc<TB, RB> P, uint64_t ntiles, const __grid_constant__ PeerPtrs peers) {
+    static_assert(!(C64 && PEER), "complex64 states are not sharded");
+    constexpr int kAmpShift = C64 ? 3 : 4;  // log2 bytes per amplitude in global memory
+    const char* in_b = reinterpret_cast<const char*>(in);
     constexpr int NT = TB - RB, NTHR = 1 << NT, NREG = 1 << RB, NSLOT = RB * (RB - 1) / 2;
     static_assert(NG == 1 || NG == 3, "one free-running tile per CTA, or three tile groups in a token ring");
     constexpr int RS = RB + 1, NV = 1 << RS, HS = RS / 2;  // split rounds: register qubits, reals per thread, group size
@@ -1152,7 +1192,11 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
     const uint32_t tstride = gridDim.x * NG;   // tiles between two consecutive tiles of a group
     const uint32_t tfirst = grp * gridDim.x + blockIdx.x;   // group 0 of every CTA first: few tiles spread over all SMs
     const uint32_t ntile32 = (uint32_t)ntiles;
-    if ((flags & kPassFuseLoad) && tid == 0 && tfirst < ntile32) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)tfirst << TB), mbar_u32);
+    auto issue_tile_load = [&](uint32_t tt) {
+        if constexpr (C64) bulk_load_tile_c64<TB>(tile_u32, in_b + ((uint64_t)tt << (TB + kAmpShift)), mbar_u32);
+        else bulk_load_tile<TB>(tile_u32, in + ((uint64_t)tt << TB), mbar_u32);
+    };
+    if ((flags & kPassFuseLoad) && tid == 0 && tfirst < ntile32) issue_tile_load(tfirst);
 
     // every group of a CTA runs the same number of iterations: the token ring needs all of them (a group without a tile left
     // only passes the token on)
@@ -1177,8 +1221,8 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 #endif
         auto prefetch_next = [&]() {
             if (tid == 0 && !(flags & kPassNoPrefetch) && t + tstride < ntile32) {
-                if (flags & kPassPfEvictLast) prefetch_l2_bulk_evict_last(in + ((uint64_t)(t + tstride) << TB), (uint32_t)(sizeof(double2) << TB));
-                else prefetch_l2_bulk(in + ((uint64_t)(t + tstride) << TB), (uint32_t)(sizeof(double2) << TB));
+                if (flags & kPassPfEvictLast) prefetch_l2_bulk_evict_last(in_b + ((uint64_t)(t + tstride) << (TB + kAmpShift)), 1u << (TB + kAmpShift));
+                else prefetch_l2_bulk(in_b + ((uint64_t)(t + tstride) << (TB + kAmpShift)), 1u << (TB + kAmpShift));
             }
         };
         if (!(flags & (kPassPfLate | kPassFuseLoad))) prefetch_next();
@@ -1221,6 +1265,20 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                 tile_parity ^= 1u;
                 token_acquire(1);
                 XYK_TR(2);
+                if constexpr (C64) {
+                    // widen in place: every thread pulls its 2^RB float2 amplitudes out of the staging area (front of the buffer,
+                    // consecutive lanes on consecutive amplitudes), the group synchronises, then the FP64 arrival layout is written
+                    float2 f[NREG];
+#pragma unroll
+                    for (int k = 0; k < NREG; ++k) f[k] = lds_f2(tile_u32 + ((((uint32_t)k << NT) + tid) << 3));
+                    group_sync();
+#pragma unroll
+                    for (int k = 0; k < NREG; ++k) {
+                        const uint32_t x = ((uint32_t)k << NT) + tid;
+                        sts128(tile_u32 + (x + (x >> 9)) * 16u, make_double2((double)f[k].x, (double)f[k].y));
+                    }
+                    group_sync();
+                }
                 if (unb) {
                     if constexpr (UNB) {
                         uint32_t st[RS];
@@ -1274,7 +1332,12 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
                     for (int k = 0; k < NREG; ++k) {
                         const uint32_t hi = pad_slot((uint32_t)k << NT);  // constant after unrolling
-                        cp_async16(&tile[ld_slot + hi], src + ((uint32_t)k << NT) + tid);
+                        if constexpr (C64) {
+                            const float2 f = __ldg(reinterpret_cast<const float2*>(in_b) + ((uint64_t)t << TB) + ((uint32_t)k << NT) + tid);
+                            tile[ld_slot + hi] = make_double2((double)f.x, (double)f.y);
+                        } else {
+                            cp_async16(&tile[ld_slot + hi], src + ((uint32_t)k << NT) + tid);
+                        }
                     }
                     cp_async_wait_all();
                     group_sync();
@@ -1330,7 +1393,7 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
             // the last round holds the tile in registers: the buffer is free for the next tile
             if ((flags & kPassFuseLoad) && (flags & kPassFuseStore) && r == nr - 1) {
                 group_sync();
-                if (tid == 0 && t + tstride < ntile32) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)(t + tstride) << TB), mbar_u32);
+                if (tid == 0 && t + tstride < ntile32) issue_tile_load(t + tstride);
             }
 
             // ---------------- diagonal phase (complex round 0 only) ----------------
@@ -1446,17 +1509,19 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                     }
                 } else {
                     // per-thread byte pointer once per tile + warp-uniform byte offsets of the register bits
-                    char* pb = reinterpret_cast<char*>(out) + (dbase << 4);
+                    char* pb = reinterpret_cast<char*>(out) + (dbase << kAmpShift);
+                    using sreal = typename std::conditional<C64, float, double>::type;    // storage scalar
+                    using scplx = typename std::conditional<C64, float2, double2>::type;  // storage amplitude
                     if (unb) {
                         if constexpr (UNB) {
-                            split_global_store<(UNB ? UNB : 2), RS, NV, PEER>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
+                            split_global_store<(UNB ? UNB : 2), RS, NV, PEER, C64>(v, out, peers, P.nq, dbase, P.last_reg_out, half, smask);
                         }
                     } else if (split) {
                         // eight per-thread pointers over the three high register bits (component by their parity) and
                         // eight warp-uniform 32-bit index offsets over the three low bits: one IMAD.WIDE per store
-                        double* q0 = reinterpret_cast<double*>(pb) + half;        // elements with f = 0: component `half`
-                        double* q1 = reinterpret_cast<double*>(pb) + (1u - half); // elements with f = 1: the other component
-                        double* bq[8];
+                        sreal* q0 = reinterpret_cast<sreal*>(pb) + half;        // elements with f = 0: component `half`
+                        sreal* q1 = reinterpret_cast<sreal*>(pb) + (1u - half); // elements with f = 1: the other component
+                        sreal* bq[8];
                         uint32_t lo2[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -1472,10 +1537,10 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
                         for (int j = 0; j < NV; ++j) {
                             const bool fj = __builtin_popcount(j >> HS) & 1;
-                            __stcs(bq[j >> HS] + lo2[j & ((1 << HS) - 1)], fj ? flip_sign(v[j], smask) : v[j]);
+                            __stcs(bq[j >> HS] + lo2[j & ((1 << HS) - 1)], (sreal)(fj ? flip_sign(v[j], smask) : v[j]));
                         }
                     } else {
-                        double2* bq[8];
+                        scplx* bq[8];
                         uint32_t lo[4];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
@@ -1483,12 +1548,17 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
                             for (int k = 0; k < 3; ++k)
                                 if ((c >> k) & 1) hi += P.st_reg_idx[2 + k];
-                            bq[c] = reinterpret_cast<double2*>(pb) + hi;
+                            bq[c] = reinterpret_cast<scplx*>(pb) + hi;
                         }
 #pragma unroll
                         for (int c = 0; c < 4; ++c) lo[c] = ((c & 1) ? P.st_reg_idx[0] : 0u) + ((c & 2) ? P.st_reg_idx[1] : 0u);
 #pragma unroll
-                        for (int j = 0; j < NREG; ++j) __stcs(bq[j >> 2] + lo[j & 3], make_double2(v[2 * j], v[2 * j + 1]));
+                        for (int j = 0; j < NREG; ++j) {
+                            scplx a;
+                            a.x = (sreal)v[2 * j];
+                            a.y = (sreal)v[2 * j + 1];
+                            __stcs(bq[j >> 2] + lo[j & 3], a);
+                        }
                     }
                 }
                 token_release(0);
@@ -1559,12 +1629,12 @@ tile_pass_kernel(const double2* __restrict__ in, double2* __restrict__ out,
                         lk |= 1u << P.st_lsrc[NT + b];
                         dk |= 1ull << P.st_odst[NT + b];
                     }
-                store_out<PEER>(out, peers, P.nq, dbase + dk, tile[st_l + pad_slot(lk)]);
+                store_out<PEER, C64>(out, peers, P.nq, dbase + dk, tile[st_l + pad_slot(lk)]);
             }
             token_release(0);
             if (flags & kPassFuseLoad) {
                 group_sync();
-                if (tid == 0 && t + tstride < ntile32) bulk_load_tile<TB>(tile_u32, in + ((uint64_t)(t + tstride) << TB), mbar_u32);
+                if (tid == 0 && t + tstride < ntile32) issue_tile_load(t + tstride);
             }
         }
     }

@@ -280,9 +280,12 @@ C64_FID_TOL = 1e-5   # stated bound of the complex64 variant: fidel
 C64_R_TOL = 1e-4     # |dR| <= 1e-4 for runs of <= 25 000 gates; coefficients and reductions stay double
 
 
-@pytest.mark.parametrize("n,reps", [(14, 4), (20, 2), (24, 1)])
-def test_complex64_state_within_stated_bound(n, reps):
-    """complex64 state (8 B per amplitude, gate-by-gate kernels, FP64 coefficients / accumulation) vs the FP64 C oracle"""
+@pytest.mark.parametrize("n,reps,order,engine", [(14, 4, 1, "simple"), (14, 4, 1, "tiled"), (13, 2, 2, "tiled"), (16, 3, 2, "tiled"),
+                                                 (20, 2, 1, "tiled"), (24, 1, 1, "tiled"), (24, 1, 1, "simple")])
+def test_complex64_state_within_stated_bound(n, reps, order, engine):
+    """complex64 state (8 B per amplitude in HBM; FP64 coefficients, on-chip arithmetic and reductions) vs the FP64 C
+    oracle: gate-by-gate kernels and the fused tile passes (float2 tiles widened to FP64 in shared memory, narrowed in the
+    fused store)"""
     import ctypes
     import os
 
@@ -290,20 +293,23 @@ def test_complex64_state_within_stated_bound(n, reps):
     Kc, wc = oc.canonicalise(n, K, w)
     with XYKEngine(n, dtype="complex64") as eng:
         eng.set_problem(Kc, wc)
+        eng.set_engine(engine)
         eng.init_product_state()
-        eng.apply_layers(0.1, 1, reps)
+        eng.apply_layers(0.1, order, reps)
         R, _ = eng.order_parameter()
         ex, ey = eng.xy_expectations()
         got = eng.get_state()
         nrm = eng.norm2()
+        st = eng.stats()
     assert got.dtype == np.complex64
+    assert (st["pass_launches"] > 0) == (engine == "tiled")
     so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_build", "libxyoracle.so")
     lib = ctypes.CDLL(so)
     dp = ctypes.POINTER(ctypes.c_double)
     psi = np.zeros(2 << n)
     lib.xyo_init_state(n, wc.ctypes.data_as(dp), psi.ctypes.data_as(dp))
     lib.xyo_evolve.argtypes = [ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_int, dp]
-    lib.xyo_evolve(n, np.ascontiguousarray(Kc).ctypes.data_as(dp), wc.ctypes.data_as(dp), 0.1, reps, 1, psi.ctypes.data_as(dp))
+    lib.xyo_evolve(n, np.ascontiguousarray(Kc).ctypes.data_as(dp), wc.ctypes.data_as(dp), 0.1, reps, order, psi.ctypes.data_as(dp))
     ref = psi.view(np.complex128)
     assert 1.0 - oc.fidelity(got.astype(np.complex128), ref) < C64_FID_TOL
     Rref, _ = oc.order_parameter(ref, n)
