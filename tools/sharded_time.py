@@ -4,6 +4,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch, torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _devlib import use_dev_library
+use_dev_library()  # tools/_build/libxyk_exp.so, or the build named by XYK_LIB_AB
 from oracle import xy_oracle as oc
 from scpn_quantum_control_b200.sharded import ShardedXYKEngine
 
