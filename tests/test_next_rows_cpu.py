@@ -59,3 +59,45 @@ def test_floquet_oracle_zero_drive_is_static_exact_evolution():
         ref = oc.exact_step(ref, H, (2 * np.pi / 2.0) / 6)
     assert 1 - oc.fidelity(psi, ref) < 1e-12
     assert out["R_values"][0] == pytest.approx(1.0)
+
+
+def test_floquet_host_helpers_match_the_oracle():
+    from scpn_quantum_control_b200.floquet_kuramoto import DTC_SUBHARMONIC_THRESHOLD, _phase_coherence, _subharmonic_ratio
+
+    rng = np.random.default_rng(8)
+    assert DTC_SUBHARMONIC_THRESHOLD == 0.1
+    for m in (3, 16, 37, 160):
+        sig = rng.uniform(0, 1, m) + 0.3 * np.cos(np.arange(m) * 0.7)
+        assert _subharmonic_ratio(sig, 2.0, 0.1) == pytest.approx(on.subharmonic_ratio(sig, 2.0, 0.1), rel=1e-14, abs=0)
+    assert _subharmonic_ratio(np.ones(10), 2.0, 0.1) == 0.0
+    psi = oc.initial_state(oc.OMEGA_N_16[:5])
+    ex, ey = oc.xy_expectations(psi, 5)
+    assert _phase_coherence(ex, ey) == pytest.approx(on.phase_coherence_R(psi, 5), abs=1e-15)
+
+
+def test_benchmark_caller_shims_validate_like_the_reference():
+    from scpn_quantum_control_b200 import benchmarks as bm
+
+    with pytest.raises(ValueError, match="n_oscillators must be an integer >= 2"):
+        bm.quantum_trotter_row(1)
+    with pytest.raises(ValueError, match="dt must be finite, positive and not exceed t_max"):
+        bm.quantum_trotter_row(4, t_max=0.1, dt=0.2)
+    with pytest.raises(ValueError, match="trotter_per_step must be an integer >= 1"):
+        bm.quantum_trotter_row(4, trotter_per_step=0)
+    row = bm.ComparisonMethodRow("quantum_trotter", "x", False, None, None, 0.0, "why")
+    assert row.to_dict()["unavailable_reason"] == "why" and list(row.to_dict())[0] == "method"
+    assert bm.statevector_scaling_row(20, max_statevector_qubits=16) == {
+        "n_qubits": 20, "baseline": "gpu_statevector", "status": "skipped", "skip_reasons": ["size gate"]}
+
+
+def test_solver_rejects_bad_next_row_arguments():
+    from scpn_quantum_control_b200 import QuantumKuramotoSolver
+
+    K, w = oc.paper27_K(4), oc.OMEGA_N_16[:4]
+    with pytest.raises(ValueError, match="evolution must be"):
+        QuantumKuramotoSolver(4, K, w, evolution="magic")
+    with pytest.raises(ValueError, match="anisotropy_delta must be finite"):
+        QuantumKuramotoSolver(4, K, w, anisotropy_delta=float("nan"))
+    with pytest.raises(ValueError, match="evolution='chebyshev' needs a single-device complex128 state"):
+        QuantumKuramotoSolver(4, K, w, evolution="chebyshev", dtype="complex64")
+    assert QuantumKuramotoSolver(4, K, w, anisotropy_delta=1e-16).anisotropy_delta == 0.0  # below the reference's sparsity threshold
