@@ -328,3 +328,47 @@ def test_complex64_solver_run():
     _, RT = oc.run(n, K, w, 0.4, 0.1, 3, order=1, mode="T")
     assert res.metadata["dtype"] == "complex64"
     assert np.abs(res["R"] - RT).max() < C64_R_TOL
+
+
+def test_next_rows_at_scale_properties():
+    """size-independent properties where no CPU oracle is cheap: XXZ through the tiled engine at n = 26 (norm, <sum Z>
+    conserved by every XX+YY+ZZ term, order-2 echo back to the product state), the Chebyshev step at n = 24 (norm, <sum Z>,
+    forward-backward echo) and the complex64 tile passes at n = 27 (echo within the stated bound)"""
+    n = 26
+    K, w = oc.random_problem(n, 2600)
+    theta = np.mod(w, 2 * np.pi)
+    with XYKEngine(n) as eng:
+        eng.set_problem(K, w, 0.6)
+        eng.set_engine("tiled")
+        eng.init_product_state()
+        eng.apply_layers(0.05, 2, 1)
+        assert abs(eng.norm2() - 1.0) < 1e-10
+        assert abs(eng.z_expectations().sum() - np.cos(theta).sum()) < 1e-9
+        eng.apply_layers(-0.05, 2, 1)
+        ex, ey = eng.xy_expectations()
+        assert max(np.abs(ex - np.sin(theta)).max(), np.abs(ey).max()) < 1e-9
+        assert eng.stats()["pass_launches"] > 0
+    n = 24
+    K, w = oc.random_problem(n, 2400)
+    theta = np.mod(w, 2 * np.pi)
+    with XYKEngine(n) as eng:
+        eng.set_problem(K, w)
+        eng.init_product_state()
+        terms = eng.exact_step(0.02, 1e-14)
+        assert terms > 3 and abs(eng.norm2() - 1.0) < 1e-10
+        assert abs(eng.z_expectations().sum() - np.cos(theta).sum()) < 1e-9
+        eng.exact_step(-0.02, 1e-14)
+        ex, ey = eng.xy_expectations()
+        assert max(np.abs(ex - np.sin(theta)).max(), np.abs(ey).max()) < 1e-9
+    n = 27
+    K, w = oc.random_problem(n, 2700)
+    theta = np.mod(w, 2 * np.pi)
+    with XYKEngine(n, dtype="complex64") as eng:
+        eng.set_problem(K, w)
+        eng.set_engine("tiled")
+        eng.init_product_state()
+        eng.apply_layers(0.05, 2, 1)
+        eng.apply_layers(-0.05, 2, 1)
+        ex, ey = eng.xy_expectations()
+        assert max(np.abs(ex - np.sin(theta)).max(), np.abs(ey).max()) < C64_R_TOL
+        assert abs(eng.norm2() - 1.0) < 1e-4
