@@ -194,6 +194,12 @@ int xyk_enable_timing(xyk_handle h, int on);
 int64_t xyk_plan_describe(int n_local, int dtype, const double *K, const double *omega, int n,
                           double delta, int order, int reps, char *buf, int64_t cap);
 
+/* Schedule compiler, host only: the intermediate results of its first `upto_stage` stages (1: tile search, 2: + round
+ * search, 3: + layouts) of a single-device program as JSON -- the unit-test view of the compiler.  Same return
+ * convention as xyk_plan_describe. */
+int64_t xyk_plan_stages(const double *K, const double *omega, int n, double delta, int order, int reps,
+                        int upto_stage, char *buf, int64_t cap);
+
 /* Batched parameter sweep: B independent n-qubit (n <= 12) problems evolved concurrently,
  * one CTA per problem with the whole state in shared memory.
  *   K: double[B*n*n], omega: double[B*n], step_sizes: double[m] (shared grid),

@@ -87,6 +87,10 @@ PROTOTYPES = {
     "xyk_stream": (c_int, [c_void_p, POINTER(c_void_p)]),
     "xyk_get_stats": (c_int, [c_void_p, POINTER(XYKStats)]),
     "xyk_enable_timing": (c_int, [c_void_p, c_int]),
+    "xyk_plan_stages": (
+        c_int64,
+        [POINTER(c_double), POINTER(c_double), c_int, c_double, c_int, c_int, c_int, c_char_p, c_int64],
+    ),
     "xyk_plan_describe": (
         c_int64,
         [c_int, c_int, POINTER(c_double), POINTER(c_double), c_int, c_double, c_int, c_int, c_char_p, c_int64],

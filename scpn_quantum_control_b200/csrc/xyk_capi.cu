@@ -1778,6 +1778,29 @@ int64_t xyk_plan_describe(int n_local, int dtype, const double* K, const double*
     }
 }
 
+int64_t xyk_plan_stages(const double* K, const double* omega, int n, double delta, int order, int reps, int upto_stage, char* buf,
+                        int64_t cap) {
+    if (n < 1 || n > kMaxQ || !K || !omega) return -1;
+    try {
+        std::vector<PairTerm> pairs;
+        std::vector<ZTerm> z;
+        std::vector<double> Ks;
+        build_terms(n, K, omega, pairs, z, Ks);
+        std::vector<Segment> segs = build_sequence(pairs, delta, order, reps, nullptr);
+        SchedConfig cfg;
+        cfg.TB = kTB;
+        cfg.RB = kRB;
+        cfg.max_rounds = kMaxRounds;
+        apply_env(cfg);
+        const std::string js = plan_stages_to_json(n, segs, cfg, upto_stage);
+        if (buf && cap > (int64_t)js.size()) std::memcpy(buf, js.c_str(), js.size() + 1);
+        return (int64_t)js.size() + 1;
+    } catch (const std::exception& e) {
+        g_global_error = e.what();
+        return -1;
+    }
+}
+
 int xyk_batch_run(int device, int n, int B, const double* K, const double* omega, const double* step_sizes, int m,
                   int reps, int order, double* R_out, void* final_states) {
     return small_batch_run(device, n, B, K, omega, step_sizes, m, reps, order, R_out, final_states, g_global_error);

@@ -132,6 +132,10 @@ inline int lane_class(int p) { return p % 3; }
 
 std::string plan_to_json(const Plan& plan);
 
+// Unit-test view of the schedule compiler: the intermediate results of its first `upto` stages (1: tile search, 2: + round
+// search, 3: + layouts) as JSON.
+std::string plan_stages_to_json(int nq, const std::vector<Segment>& segs, const SchedConfig& cfg, int upto);
+
 // ---- sharded state (top g physical bits = rank): local programs separated by exchanges ----
 struct ShardOp {
     bool is_exchange = false;

@@ -152,17 +152,63 @@ void round_closure(const std::vector<Gate>& g, const std::vector<int>& cand, con
 
 int popc(uint64_t x) { return __builtin_popcountll(x); }
 
-}  // namespace
 
-Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& cfg) {
-    if (nq < 1 || nq > kMaxQ) throw std::runtime_error("compile_plan: bad qubit count");
-    const int TB = std::min(cfg.TB, nq);
-    const int RB = std::min(cfg.RB, TB);
+std::mutex g_memo_mutex;  // guards the process-wide tile-sequence and round-decomposition memos (held for a whole compile)
+
+// The schedule compiler: four stages over shared state.
+//   prepare()        gate lists per segment (sweep directions), merged diagonal phases, configuration signature
+//   choose_tiles()   1. the tile (set of TB logical qubits) of every pass, segment by segment
+//   search_rounds()  2. the register rounds of every pass
+//   assign_layouts() 3. the order of the qubits on the physical bits before every pass
+//   emit_passes()    4. PlanPass descriptors (thread / lane / warp assignment, coefficients), over-long passes cut in pieces
+// Each stage can be exercised on its own through compile_plan_stages() (tests/test_schedule_cpu.py).
+struct PlanCompiler {
+    struct RawPass {
+        uint64_t tmask;
+        int seg;
+        std::vector<int> gate_idx;  // indices into the segment's gate list
+        bool has_phase;
+    };
+    struct RawRound {
+        uint64_t rmask = 0;
+        std::vector<int> cidx;  // indices into the pass's gate_idx
+        bool reverse = false;
+        bool split = false;     // split round: gates only between lmask and rmask & ~lmask
+        uint64_t lmask = 0;
+    };
+
+    const int nq;
+    const std::vector<Segment>& segs;
+    const SchedConfig& cfg;
+    int TB = 0, RB = 0;
+    int RS = 0;                                // register qubits of a split round
     Plan plan;
+    std::string cfg_sig;                       // everything of the configuration the memoised searches depend on
+    std::vector<std::vector<Gate>> sg;         // prepare: gates per segment
+    std::vector<double> zeff;                  // prepare: diagonal phase in front of every segment with gates
+    std::vector<RawPass> raw;                  // stage 1: tiles and their gates
+    int P = 0;                                 // number of passes
+    std::vector<std::vector<RawRound>> rr;     // stage 2: rounds per pass
+    std::vector<uint64_t> rlast, rfirst;       // stage 2: register qubits of the last / first round per pass
+    int c_lane = 0;
+    std::vector<std::vector<int>> layouts;     // stage 3: logical -> physical before pass p (P + 1 entries)
+    std::vector<int> nshared, nfree;
+
+    PlanCompiler(int nq_, const std::vector<Segment>& segs_, const SchedConfig& cfg_) : nq(nq_), segs(segs_), cfg(cfg_) {}
+
+    int prev_index(int p) const {
+        if (p > 0) return p - 1;
+        return (cfg.cyclic && P > 1) ? P - 1 : -1;
+    }
+
+    void prepare() {
+    if (nq < 1 || nq > kMaxQ) throw std::runtime_error("compile_plan: bad qubit count");
+    TB = std::min(cfg.TB, nq);
+    RB = std::min(cfg.RB, TB);
+    RS = RB + 1;
     plan.nq = nq;
     plan.TB = TB;
     plan.RB = RB;
-    std::string cfg_sig;  // everything of the configuration the memoised searches depend on
     {
         std::ostringstream os;
         os << nq << '/' << TB << '/' << RB << '/' << cfg.need_shared << '/' << cfg.lane_bits << '/' << cfg.fuse_io << cfg.split_rounds << cfg.cyclic
@@ -172,15 +218,8 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         cfg_sig = os.str();
     }
 
-    // ---- 1. choose the tile (set of TB logical qubits) of every pass, segment by segment ----
-    struct RawPass {
-        uint64_t tmask;
-        int seg;
-        std::vector<int> gate_idx;  // indices into the segment's gate list
-        bool has_phase;
-    };
-    std::vector<RawPass> raw;
-    std::vector<std::vector<Gate>> sg(segs.size());
+
+    sg.assign(segs.size(), {});
     for (size_t s = 0; s < segs.size(); ++s) {
         int last_sweep = -1, sweep_no = -1;
         for (size_t k = 0; k < segs[s].gates.size(); ++k) {
@@ -210,7 +249,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     }
 
     // diagonal phases of gate-free segments commute with everything diagonal: merge them forward
-    std::vector<double> zeff(segs.size(), 0.0);
+    zeff.assign(segs.size(), 0.0);
     {
         double carry = 0.0;
         for (size_t s = 0; s < segs.size(); ++s) {
@@ -223,7 +262,10 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         plan.trailing_ztau = carry;
         plan.has_trailing_phase = carry != 0.0;
     }
+    }
 
+    // ---- 1. choose the tile (set of TB logical qubits) of every pass, segment by segment ----
+    void choose_tiles() {
     const uint64_t all_mask = nq >= 64 ? ~0ull : ((1ull << nq) - 1);
     // qubits of the program's first tile ranked by how late the first pass uses them: when the last tile
     // has to share qubits with the first one (cyclic programs), the late ones are free to become the
@@ -283,8 +325,6 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     };
     // process-wide: the same gate pattern (another step size, another handle) reuses the searched tile sequence
     static std::map<std::string, TileMemo> tile_memo;
-    static std::mutex tile_memo_mutex;
-    std::lock_guard<std::mutex> tile_memo_lock(tile_memo_mutex);
     if (tile_memo.size() > 4096) tile_memo.clear();
     size_t last_seg_with_gates = 0;
     for (size_t s = 0; s < segs.size(); ++s)
@@ -583,6 +623,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         }
         if (raw.empty()) first_tile = 0;
     }
+    }
 
     // ---- 2. register rounds of every pass (sets of RB qubits + the gates they execute) ----
     // The LAST round of a pass is chosen first (closure over the reversed sequence) and the FIRST
@@ -590,28 +631,18 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // hold in registers: the qubits that stay out of both become the lowest physical bits of the
     // layout between the two passes, which lets the last round store and the next first round
     // load global memory directly with lanes on contiguous addresses.
-    const int P = (int)raw.size();
+    void search_rounds() {
+    P = (int)raw.size();
     auto next_tile = [&](int p) -> uint64_t {
         if (P == 1 && cfg.cyclic) return 0;
         if (p + 1 < P) return raw[p + 1].tmask;
         return cfg.cyclic ? raw[0].tmask : cfg.next_tile_hint;
     };
-    auto prev_index = [&](int p) -> int {
-        if (p > 0) return p - 1;
-        return (cfg.cyclic && P > 1) ? P - 1 : -1;
-    };
-    struct RawRound {
-        uint64_t rmask = 0;
-        std::vector<int> cidx;  // indices into the pass's gate_idx
-        bool reverse = false;
-        bool split = false;     // split round: gates only between lmask and rmask & ~lmask
-        uint64_t lmask = 0;
-    };
-    const int RS = RB + 1;  // register qubits of a split round
     const bool can_split = cfg.split_rounds && (RS % 2 == 0) && TB - RS >= 3 && RS <= 8;
-    std::vector<std::vector<RawRound>> rr(P);
-    std::vector<uint64_t> rlast(P, 0), rfirst(P, 0);
-    const int c_lane = std::min(cfg.lane_bits, TB);
+    rr.assign(P, {});
+    rlast.assign(P, 0);
+    rfirst.assign(P, 0);
+    c_lane = std::min(cfg.lane_bits, TB);
 
     auto rev_round_closure = [&](const std::vector<Gate>& g, const std::vector<int>& cand,
                                  const std::vector<char>& cdone, uint64_t rmask, std::vector<int>& out) {
@@ -1031,6 +1062,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         memo[key] = RoundsMemo{last_round[p], rr[p]};
     }
     for (int p = 0; p < P; ++p) rr[p].push_back(last_round[p]);
+    }
 
     // ---- 3. layouts: tile qubits of pass p sit on physical bits [0, TB) before pass p ----
     // order: qubits shared with the previous tile that neither the previous last round nor this
@@ -1039,6 +1071,7 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
     // `prev_layout` (positions of the qubits before the previous pass, empty if unknown): the three qubits that land on
     // output bits 0..2 of the previous pass are the low lane bits of its last round's fused store, and that round READS them
     // from shared-memory positions prev_layout[q]; three different bank classes there make those reads conflict free.
+    void assign_layouts() {
     auto make_layout = [&](int p, std::vector<int>& perm, int& nshared, int& nfree, const std::vector<int>& prev_layout) {
         const uint64_t tile = raw[p].tmask;
         const int pm = prev_index(p);
@@ -1088,8 +1121,9 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         for (int q = 0; q < nq; ++q)
             if (!((tile >> q) & 1)) perm[q] = pos++;
     };
-    std::vector<std::vector<int>> layouts(P + 1);
-    std::vector<int> nshared(P + 1, 0), nfree(P + 1, 0);
+    layouts.assign(P + 1, {});
+    nshared.assign(P + 1, 0);
+    nfree.assign(P + 1, 0);
     {
         const std::vector<int> none;
         for (int p = 0; p < P; ++p) make_layout(p, layouts[p], nshared[p], nfree[p], p > 0 ? layouts[p - 1] : none);
@@ -1156,8 +1190,10 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         plan.last_tile_mask = raw[P - 1].tmask;
         plan.last_rlast_mask = rlast[P - 1];
     }
+    }
 
     // ---- 4. emit passes ----
+    void emit_passes() {
     for (int p = 0; p < P; ++p) {
         const RawPass& rp = raw[p];
         const std::vector<Gate>& g = sg[rp.seg];
@@ -1414,7 +1450,81 @@ Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& c
         }
         plan.passes.swap(out);
     }
-    return plan;
+    }
+};
+
+}  // namespace
+
+// Intermediate results of the first `upto` stages (1: tiles, 2: + rounds, 3: + layouts) as JSON: the unit-test view of the
+// schedule compiler (tests/test_schedule_stages_cpu.py).
+std::string plan_stages_to_json(int nq, const std::vector<Segment>& segs, const SchedConfig& cfg, int upto) {
+    std::lock_guard<std::mutex> memo_lock(g_memo_mutex);
+    PlanCompiler pc(nq, segs, cfg);
+    pc.prepare();
+    pc.choose_tiles();
+    if (upto >= 2) pc.search_rounds();
+    if (upto >= 3) pc.assign_layouts();
+    auto qubits = [](uint64_t m) {
+        std::ostringstream os;
+        os << '[';
+        bool first = true;
+        for (int q = 0; q < 64; ++q)
+            if ((m >> q) & 1) {
+                os << (first ? "" : ",") << q;
+                first = false;
+            }
+        os << ']';
+        return os.str();
+    };
+    std::ostringstream os;
+    os << "{\"nq\":" << nq << ",\"TB\":" << pc.TB << ",\"RB\":" << pc.RB << ",\"RS\":" << pc.RS << ",\"need_shared\":" << std::min(cfg.need_shared, pc.TB)
+       << ",\"stages\":" << std::min(std::max(upto, 1), 3) << ",\"passes\":[";
+    for (size_t p = 0; p < pc.raw.size(); ++p) {
+        const auto& rp = pc.raw[p];
+        const auto& g = pc.sg[rp.seg];
+        os << (p ? "," : "") << "{\"tile\":" << qubits(rp.tmask) << ",\"seg\":" << rp.seg << ",\"has_phase\":" << (rp.has_phase ? 1 : 0) << ",\"gates\":[";
+        for (size_t k = 0; k < rp.gate_idx.size(); ++k)
+            os << (k ? "," : "") << '[' << rp.gate_idx[k] << ',' << g[rp.gate_idx[k]].i << ',' << g[rp.gate_idx[k]].j << ',' << g[rp.gate_idx[k]].sweep << ']';
+        os << ']';
+        if (upto >= 2) {
+            os << ",\"rounds\":[";
+            for (size_t r = 0; r < pc.rr[p].size(); ++r) {
+                const auto& R = pc.rr[p][r];
+                os << (r ? "," : "") << "{\"reg\":" << qubits(R.rmask) << ",\"split\":" << (R.split ? 1 : 0) << ",\"left\":" << qubits(R.split ? R.lmask : 0)
+                   << ",\"gates\":[";
+                for (size_t k = 0; k < R.cidx.size(); ++k) os << (k ? "," : "") << rp.gate_idx[R.cidx[k]];
+                os << "]}";
+            }
+            os << ']';
+        }
+        if (upto >= 3) {
+            os << ",\"layout\":[";
+            for (int q = 0; q < nq; ++q) os << (q ? "," : "") << pc.layouts[p][q];
+            os << "],\"n_shared_in\":" << pc.nshared[p];
+        }
+        os << '}';
+    }
+    os << "],\"segments\":[";
+    for (size_t s = 0; s < pc.sg.size(); ++s) os << (s ? "," : "") << pc.sg[s].size();
+    os << ']';
+    if (upto >= 3 && !pc.layouts.empty()) {
+        os << ",\"final_layout\":[";
+        for (size_t q = 0; q < pc.layouts.back().size(); ++q) os << (q ? "," : "") << pc.layouts.back()[q];
+        os << ']';
+    }
+    os << '}';
+    return os.str();
+}
+
+Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& cfg) {
+    std::lock_guard<std::mutex> memo_lock(g_memo_mutex);
+    PlanCompiler pc(nq, segs, cfg);
+    pc.prepare();
+    pc.choose_tiles();
+    pc.search_rounds();
+    pc.assign_layouts();
+    pc.emit_passes();
+    return std::move(pc.plan);
 }
 
 std::vector<ShardOp> compile_sharded(int n, const std::vector<int>& global_qubits, const std::vector<Segment>& segs,

@@ -261,3 +261,17 @@ def batch_run(K: np.ndarray, omega: np.ndarray, step_sizes: np.ndarray, reps: in
             raise ValueError(msg)
         raise RuntimeError(f"xyk_batch_run failed ({rc}): {msg}")
     return (R, states) if return_states else R
+
+
+def plan_stages(K: np.ndarray, omega: np.ndarray, delta: float, order: int, reps: int, upto_stage: int = 3) -> dict:
+    """Host-only: intermediate results of the schedule compiler's stages (1: tiles, 2: + rounds, 3: + layouts)."""
+    lib = _lib.load()
+    K = np.ascontiguousarray(K, dtype=np.float64)
+    omega = np.ascontiguousarray(omega, dtype=np.float64)
+    n = omega.shape[0]
+    need = lib.xyk_plan_stages(_dptr(K), _dptr(omega), n, float(delta), order, reps, upto_stage, None, 0)
+    if need < 0:
+        raise RuntimeError(_lib.last_error(None))
+    buf = ctypes.create_string_buffer(int(need))
+    lib.xyk_plan_stages(_dptr(K), _dptr(omega), n, float(delta), order, reps, upto_stage, buf, need)
+    return json.loads(buf.value.decode())
