@@ -372,3 +372,32 @@ def test_next_rows_at_scale_properties():
         ex, ey = eng.xy_expectations()
         assert max(np.abs(ex - np.sin(theta)).max(), np.abs(ey).max()) < C64_R_TOL
         assert abs(eng.norm2() - 1.0) < 1e-4
+
+
+def test_complex64_next_row_kernels():
+    """the float instantiations of the ZZ diagonal sweep, the per-pair ZZ gate and the Ry layer (complex64 storage)"""
+    n = 13
+    K, w = oc.random_problem(n, 1300)
+    Kc, wc = oc.canonicalise(n, K, w)
+    delta = 0.5
+    z, p = on.term_list_xxz(Kc, wc, delta)
+    ang = np.linspace(-0.3, 0.3, n)
+    for engine in ("tiled", "simple"):
+        with XYKEngine(n, dtype="complex64") as eng:
+            eng.set_problem(Kc, wc, delta)
+            eng.set_engine(engine)
+            eng.init_product_state()
+            eng.apply_layers(0.1, 2, 1)
+            eng.apply_ry(ang)
+            got = eng.get_state().astype(np.complex128)
+        psi = oc.initial_state(wc)
+        psi = (on.layer_order2_xxz_grouped if engine == "tiled" else on.layer_order2_xxz)(psi, n, z, p, 0.1)
+        for q in range(n):
+            on.apply_ry(psi, n, q, float(ang[q]))
+        assert 1.0 - oc.fidelity(got, psi) < C64_FID_TOL, engine
+        assert np.abs(got - psi).max() < 1e-5, engine   # global phase of the ZZ terms kept
+    with XYKEngine(n, dtype="complex64") as eng:
+        eng.set_problem(Kc, wc)
+        eng.init_product_state()
+        with pytest.raises(RuntimeError):
+            eng.exact_step(0.1)   # the Chebyshev step needs a complex128 state
