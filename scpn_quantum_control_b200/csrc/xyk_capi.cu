@@ -1229,16 +1229,21 @@ int xyk_term_counts(xyk_handle h, int* n_pairs, int* n_z) {
     return XYK_OK;
 }
 
-int xyk_init_product_state(xyk_handle h) {
-    if (!h) return XYK_ERR_INVALID;
+// product state of the problem's frequencies, written directly in `layout` (logical -> physical; null: canonical order)
+static int init_product_in_layout(xyk_handle h, const std::vector<int>* layout) {
     XYK_CHECK(h, h->have_problem, XYK_ERR_STATE, "no problem set");
     XYK_CUDA(h, cudaSetDevice(h->device));
     // keep global bits where they are, local qubits in canonical order
-    for (int q = 0; q < h->n; ++q) h->perm[q] = q;
+    for (int q = 0; q < h->n; ++q) h->perm[q] = layout ? (*layout)[q] : q;
     int rc = h->dtype == 0 ? launch_init<double>(h) : launch_init<float>(h);
     if (rc) return rc;
     h->state_valid = true;
     return XYK_OK;
+}
+
+int xyk_init_product_state(xyk_handle h) {
+    if (!h) return XYK_ERR_INVALID;
+    return init_product_in_layout(h, nullptr);
 }
 
 int xyk_init_product_angles(xyk_handle h, const double* angles) {
@@ -1615,7 +1620,21 @@ int xyk_run(xyk_handle h, const double* step_sizes, int m, int reps, int order, 
     if (!h || !R_out || (m > 0 && !step_sizes)) return XYK_ERR_INVALID;
     XYK_CHECK(h, m >= 0, XYK_ERR_INVALID, "m must be >= 0");
     XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "xyk_run drives a single-device state (sharded states are driven by the host)");
-    int rc = xyk_init_product_state(h);
+    // the state is prepared directly in the start layout of the first step's pass program: no re-layout sweep before it
+    std::vector<int> start_layout;
+    const bool formula_ok = (order == 1 || order == 2 || order == 4 || order == 6) && reps >= 1 && std::isfinite(m > 0 ? step_sizes[0] : 0.0);
+    if (m > 0 && formula_ok && h->have_problem && use_tiled(h)) {   // (bad arguments are reported by xyk_apply_layers below)
+        try {
+            std::shared_ptr<Program> prog = get_program(h, step_sizes[0], order, reps);
+            if (!prog->plan.passes.empty()) {
+                start_layout.assign(h->n, 0);
+                for (int l = 0; l < prog->plan.nq; ++l) start_layout[prog->loc2log[l]] = prog->plan.start_perm[l];
+            }
+        } catch (const std::exception& e) {
+            return fail(h, XYK_ERR_INVALID, e.what());
+        }
+    }
+    int rc = init_product_in_layout(h, start_layout.empty() ? nullptr : &start_layout);
     if (rc) return rc;
     // the whole trajectory is enqueued without a host round trip: R(t) stays on the device until the end
     double* d_R = nullptr;
