@@ -1412,7 +1412,11 @@ int xyk_z_expectations(xyk_handle h, double* exp_z) {
     XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
     XYK_CUDA(h, cudaSetDevice(h->device));
     const uint64_t dim = 1ull << h->nlocal;
-    const int grid = std::min(kRedBlocks, grid_for(h, dim, 256));
+    // power-of-two grid (z_expect_kernel): 2^T threads with nlocal - T <= 16 high bits left to the per-amplitude bookkeeping
+    int grid = 1;
+    while (grid * 2 <= kRedBlocks && (uint64_t)grid * 2 * 256 <= dim) grid *= 2;
+    while (h->nlocal - (31 - __builtin_clz((unsigned)(grid * 256))) > 16) grid *= 2;   // very large shards: more blocks than kRedBlocks
+    XYK_CHECK(h, (size_t)grid * (kMaxQ + 1) <= (size_t)kPartialDoubles, XYK_ERR_UNSUPPORTED, "z expectations: shard too large for the partial buffer");
     if (h->dtype == 0)
         z_expect_kernel<double><<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], h->nlocal, h->d_partial);
     else

@@ -429,25 +429,40 @@ __global__ void __launch_bounds__(256) xy_expect_multi_kernel(const typename cpl
 template <typename real>
 __global__ void z_expect_kernel(const typename cplx<real>::type* __restrict__ psi, int nlocal,
                                 double* __restrict__ partial /* [grid][kMaxQ+1] */) {
+    // The grid is a power of two (2^T threads in all): the low T index bits of every amplitude a thread reads are its global
+    // thread id, so only the nlocal - T high bits (the iteration counter) need per-amplitude bookkeeping -- at most kZHi
+    // conditional adds per amplitude instead of one per qubit.
+    constexpr int kZHi = 16;
     __shared__ double red[32];
     const uint64_t dim = 1ull << nlocal;
-    // per-thread: total weight and weight with bit b set, for b < nlocal (registers: dynamic loop
-    // kept rolled over b with a small local array)
-    double w1[kMaxQ];
+    const uint32_t nthreads = gridDim.x * blockDim.x;   // power of two (host)
+    const int T = 31 - __clz(nthreads);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t iters = nthreads >= dim ? 1 : (dim >> T);
+    double hi1[kZHi];   // weight with high bit T + b set
 #pragma unroll
-    for (int b = 0; b < kMaxQ; ++b) w1[b] = 0.0;
+    for (int b = 0; b < kZHi; ++b) hi1[b] = 0.0;
     double tot = 0.0;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < dim; p += (uint64_t)gridDim.x * blockDim.x) {
-        const typename cplx<real>::type a = psi[p];
-        const double pr = (double)a.x * (double)a.x + (double)a.y * (double)a.y;
-        tot += pr;
+    if (gtid < dim) {
+        for (uint64_t it = 0; it < iters; ++it) {
+            const typename cplx<real>::type a = psi[(it << T) + gtid];
+            const double pr = (double)a.x * (double)a.x + (double)a.y * (double)a.y;
+            tot += pr;
 #pragma unroll
-        for (int b = 0; b < kMaxQ; ++b) w1[b] += ((p >> b) & 1ull) ? pr : 0.0;
+            for (int b = 0; b < kZHi; ++b) hi1[b] += ((it >> b) & 1ull) ? pr : 0.0;
+        }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
     for (int b = 0; b <= kMaxQ; ++b) {
-        double v = b < kMaxQ ? w1[b < kMaxQ ? b : 0] : tot;
+        double v;
+        if (b == kMaxQ) v = tot;
+        else if (b < T) v = ((gtid >> b) & 1u) ? tot : 0.0;
+        else {
+            v = 0.0;
+#pragma unroll
+            for (int k = 0; k < kZHi; ++k)
+                if (k == b - T) v = hi1[k];
+        }
         v = warp_sum(v);
         if (lane == 0) red[warp] = v;
         __syncthreads();
