@@ -121,6 +121,11 @@ int xyk_ipc_import(xyk_handle h, int peer_rank, int which, const unsigned char *
  * reported through need_exchange != 0 (see python host).
  * Replaces: scpn_quantum_engine.all_xy_expectations (scpn_quantum_engine/src/pauli.rs:180-214). */
 int xyk_xy_expectations(xyk_handle h, double *exp_x, double *exp_y);
+/* Sharded handles with mapped peer buffers: this rank's partial sums of <X_q>, <Y_q> for the SHARDED qubits (0 for local
+ * qubits), computed by reading the partner shard through the peer mapping (NVLink) -- no qubit exchange.  Every rank calls
+ * it between two fences (all ranks idle on their state buffers); the sum over ranks is the expectation value. */
+int xyk_xy_expectations_peer(xyk_handle h, double *exp_x, double *exp_y);
+
 /* R = |sum_q (<X_q> + i<Y_q>)| / n, psi = arg.  Replaces: measure_order_parameter
  * (xy_kuramoto.py:156-185), state_order_param_sparse (pauli.rs:72-116),
  * order_param_from_statevector (sectors.rs:67-99).  Single-GPU handles only. */

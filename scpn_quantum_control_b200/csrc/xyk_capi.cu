@@ -1389,6 +1389,37 @@ int xyk_xy_expectations(xyk_handle h, double* exp_x, double* exp_y) {
     return XYK_OK;
 }
 
+int xyk_xy_expectations_peer(xyk_handle h, double* exp_x, double* exp_y) {
+    if (!h || !exp_x || !exp_y) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CHECK(h, h->world > 1 && h->peers_ready, XYK_ERR_UNSUPPORTED, "peer reads need a sharded handle with mapped peer buffers");
+    XYK_CHECK(h, h->dtype == 0, XYK_ERR_UNSUPPORTED, "sharded states are complex128");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    const uint64_t dim = 1ull << h->nlocal;
+    const int grid = std::min(kRedBlocks, grid_for(h, dim, 256));
+    XYK_CUDA(h, cudaMemsetAsync(h->d_partial, 0, sizeof(double2) * (size_t)h->n * kRedBlocks, h->stream));
+    for (int q = 0; q < h->n; ++q) {
+        if (h->perm[q] < h->nlocal) continue;
+        const int b = h->perm[q] - h->nlocal;
+        if ((h->rank >> b) & 1) continue;   // the partner with the bit clear does this pair of shards
+        const double2* peer = (const double2*)h->peer_buf[h->rank | (1 << b)][h->cur];
+        XYK_CHECK(h, peer != nullptr, XYK_ERR_STATE, "peer buffer not mapped");
+        peer_dot_kernel<<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], peer, dim, (double2*)h->d_partial + (size_t)q * kRedBlocks);
+        h->stats.kernel_launches++;
+        h->stats.state_sweeps++;
+    }
+    xy_finalize_kernel<<<h->n, 128, 0, h->stream>>>((const double2*)h->d_partial, grid, kRedBlocks, h->d_out);
+    h->stats.kernel_launches++;
+    XYK_CUDA(h, cudaGetLastError());
+    XYK_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * 2 * h->n, cudaMemcpyDeviceToHost, h->stream));
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int q = 0; q < h->n; ++q) {
+        exp_x[q] = h->h_out[2 * q];
+        exp_y[q] = h->h_out[2 * q + 1];
+    }
+    return XYK_OK;
+}
+
 int xyk_order_parameter(xyk_handle h, double* R, double* psi) {
     if (!h || !R) return XYK_ERR_INVALID;
     XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "order parameter of a sharded state is assembled by the host");

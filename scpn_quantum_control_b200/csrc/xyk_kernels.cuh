@@ -169,6 +169,22 @@ __global__ void pair_gate_kernel(typename cplx<real>::type* __restrict__ psi, in
     }
 }
 
+// Sharded qubit on rank bit b: <X_q> + i <Y_q> = 2 sum_{k} conj(psi^{(r)}_k) psi^{(r | 2^b)}_k over the ranks r with bit b clear --
+// the partner's amplitudes are READ through the peer mapping (NVLink), no exchange.  partial[blockIdx.x] = sum conj(a_k) b_k.
+__global__ void __launch_bounds__(256) peer_dot_kernel(const double2* __restrict__ mine, const double2* __restrict__ peer, uint64_t dim,
+                                                       double2* __restrict__ partial) {
+    __shared__ double red[2 * 32];
+    double v[2] = {0.0, 0.0};
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 a = mine[k];
+        const double2 b = __ldcs(peer + k);   // streamed once over NVLink
+        v[0] += a.x * b.x + a.y * b.y;
+        v[1] += a.x * b.y - a.y * b.x;
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(v[0], v[1]);
+}
+
 // ---- XXZ anisotropy: diagonal ZZ phases (bridge/knm_hamiltonian.py:196-201, term -K_ij delta Z_i Z_j) ----
 // psi_k *= exp(+i theta z_i z_j), z = 1 - 2 bit: one pair, gate-by-gate engine (reference term order XX, YY, ZZ per pair)
 template <typename real>

@@ -121,6 +121,12 @@ class XYKEngine:
         self._check(self._lib.xyk_xy_expectations(self._h, _dptr(ex), _dptr(ey)))
         return ex, ey
 
+    def xy_expectations_peer(self) -> tuple[np.ndarray, np.ndarray]:
+        """Sharded handles: this rank's partial <X_q>, <Y_q> of the sharded qubits, from peer reads (no exchange)."""
+        ex, ey = np.zeros(self.n), np.zeros(self.n)
+        self._check(self._lib.xyk_xy_expectations_peer(self._h, _dptr(ex), _dptr(ey)))
+        return ex, ey
+
     def order_parameter(self) -> tuple[float, float]:
         r, p = c_double(), c_double()
         self._check(self._lib.xyk_order_parameter(self._h, byref(r), byref(p)))

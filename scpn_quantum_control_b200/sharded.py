@@ -62,8 +62,10 @@ class ShardedXYKEngine:
         self.exchange_bytes = 0
         self.exchange_log: list[float] = []  # milliseconds per exchange
         self.barriers = 0
+        self._peers_mapped = False
         if peer_exchange:
             self._map_peer_buffers()
+            self._peers_mapped = True
 
     def _map_peer_buffers(self) -> None:
         """Exchange CUDA IPC handles of both state buffers so that a pass can store into any rank."""
@@ -155,6 +157,15 @@ class ShardedXYKEngine:
         """<X_q>, <Y_q> for every qubit (pauli.rs:180-214 semantics) of the full sharded state."""
         glob = self.global_qubits()
         ex, ey = self.eng.xy_expectations()  # partial sums over this shard; 0 for sharded qubits
+        if glob and self._peers_mapped:
+            # sharded qubits: every rank with the qubit's rank bit clear reads its partner's shard through the peer mapping
+            # (NVLink) -- no qubit exchange, the sharding stays as it is; the fence in front makes every shard final, the
+            # all-reduce behind it doubles as the fence that keeps the shards untouched until every reader is done
+            self.eng.synchronize()
+            self._dist.barrier(group=self.group)
+            gx, gy = self.eng.xy_expectations_peer()
+            tot = self._allreduce(np.concatenate([ex + gx, ey + gy]))
+            return tot[: self.n].copy(), tot[self.n:].copy()
         tot = self._allreduce(np.concatenate([ex, ey]))
         ex, ey = tot[: self.n].copy(), tot[self.n:].copy()
         if glob:
