@@ -122,7 +122,8 @@ int xyk_ipc_import(xyk_handle h, int peer_rank, int which, const unsigned char *
  * Replaces: scpn_quantum_engine.all_xy_expectations (scpn_quantum_engine/src/pauli.rs:180-214). */
 int xyk_xy_expectations(xyk_handle h, double *exp_x, double *exp_y);
 /* Sharded handles with mapped peer buffers: this rank's partial sums of <X_q>, <Y_q> for the SHARDED qubits (0 for local
- * qubits), computed by reading the partner shard through the peer mapping (NVLink) -- no qubit exchange.  Every rank calls
+ * qubits), computed by reading half of the partner shard through the peer mapping (NVLink; the two ranks of a pair split the index
+ * range) -- no qubit exchange.  Every rank calls
  * it between two fences (all ranks idle on their state buffers); the sum over ranks is the expectation value. */
 int xyk_xy_expectations_peer(xyk_handle h, double *exp_x, double *exp_y);
 

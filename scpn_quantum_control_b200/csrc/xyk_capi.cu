@@ -1401,10 +1401,11 @@ int xyk_xy_expectations_peer(xyk_handle h, double* exp_x, double* exp_y) {
     for (int q = 0; q < h->n; ++q) {
         if (h->perm[q] < h->nlocal) continue;
         const int b = h->perm[q] - h->nlocal;
-        if ((h->rank >> b) & 1) continue;   // the partner with the bit clear does this pair of shards
-        const double2* peer = (const double2*)h->peer_buf[h->rank | (1 << b)][h->cur];
+        const int upper = (h->rank >> b) & 1;   // both ranks of the pair work: the lower half of the indices here, the upper half there
+        const double2* peer = (const double2*)h->peer_buf[h->rank ^ (1 << b)][h->cur];
         XYK_CHECK(h, peer != nullptr, XYK_ERR_STATE, "peer buffer not mapped");
-        peer_dot_kernel<<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], peer, dim, (double2*)h->d_partial + (size_t)q * kRedBlocks);
+        const uint64_t k0 = upper ? dim / 2 : 0, k1 = upper ? dim : dim / 2;
+        peer_dot_kernel<<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], peer, k0, k1, upper, (double2*)h->d_partial + (size_t)q * kRedBlocks);
         h->stats.kernel_launches++;
         h->stats.state_sweeps++;
     }

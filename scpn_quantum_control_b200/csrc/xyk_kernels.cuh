@@ -170,14 +170,17 @@ __global__ void pair_gate_kernel(typename cplx<real>::type* __restrict__ psi, in
 }
 
 // Sharded qubit on rank bit b: <X_q> + i <Y_q> = 2 sum_{k} conj(psi^{(r)}_k) psi^{(r | 2^b)}_k over the ranks r with bit b clear --
-// the partner's amplitudes are READ through the peer mapping (NVLink), no exchange.  partial[blockIdx.x] = sum conj(a_k) b_k.
-__global__ void __launch_bounds__(256) peer_dot_kernel(const double2* __restrict__ mine, const double2* __restrict__ peer, uint64_t dim,
-                                                       double2* __restrict__ partial) {
+// the partner's amplitudes are READ through the peer mapping (NVLink), no exchange.  Both ranks of a pair take half of the
+// index range [k0, k1) each (the one with the bit set conjugates the PEER's amplitudes: mine_is_upper), so every rank reads
+// half a shard per sharded qubit.  partial[blockIdx.x] = sum conj(lower_k) upper_k.
+__global__ void __launch_bounds__(256) peer_dot_kernel(const double2* __restrict__ mine, const double2* __restrict__ peer, uint64_t k0, uint64_t k1,
+                                                       int mine_is_upper, double2* __restrict__ partial) {
     __shared__ double red[2 * 32];
     double v[2] = {0.0, 0.0};
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < dim; k += (uint64_t)gridDim.x * blockDim.x) {
-        const double2 a = mine[k];
-        const double2 b = __ldcs(peer + k);   // streamed once over NVLink
+    for (uint64_t k = k0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < k1; k += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 m = mine[k];
+        const double2 p = __ldcs(peer + k);   // streamed once over NVLink
+        const double2 a = mine_is_upper ? p : m, b = mine_is_upper ? m : p;
         v[0] += a.x * b.x + a.y * b.y;
         v[1] += a.x * b.y - a.y * b.x;
     }
