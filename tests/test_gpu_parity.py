@@ -398,3 +398,29 @@ def test_tile_observables_after_evolution(n):
     rx, ry = oc.xy_expectations(ref, n)
     assert np.abs(ex - rx).max() < 1e-12 and np.abs(ey - ry).max() < 1e-12
     assert np.abs(ez - oc.z_expectations(ref, n)).max() < 1e-12
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_random_coupling_patterns_through_the_tiled_engine(case):
+    """seeded random sparsity patterns (empty rows, isolated qubits, missing Z terms, negative steps) through the fused tile
+    passes vs the oracle: partial rounds, unbalanced split rounds and masks that the all-to-all problems never produce"""
+    rng = np.random.default_rng(7100 + case)
+    n = int(rng.integers(13, 17))
+    density = [0.05, 0.2, 0.5, 0.8][case % 4]
+    A = rng.uniform(0.0, 2.0, (n, n)) * (rng.uniform(size=(n, n)) < density)
+    K = np.triu(A, 1)
+    K = K + K.T
+    if case % 3 == 0:
+        q = int(rng.integers(0, n))
+        K[q, :] = 0.0
+        K[:, q] = 0.0
+    w = rng.uniform(0.1, 5.0, n)
+    if case % 2:
+        w[int(rng.integers(0, n))] = 0.0
+    order = 1 + case % 2
+    delta = [0.1, -0.07, 0.03][case % 3]
+    ref = c_oracle_evolve(n, K, w, delta, 2, order)
+    psi, R, st = engine_evolve(n, K, w, delta, 2, order, "tiled")
+    assert 1.0 - oc.fidelity(psi, ref) < FID_TOL
+    assert np.abs(psi - ref).max() < 1e-10
+    assert abs(R - oc.order_parameter(ref, n)[0]) < R_TOL
