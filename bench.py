@@ -10,6 +10,11 @@ configuration the metric "XY Trotter steps/sec at n=30" is quoted on).  With N >
 n = 30 state is sharded by its top log2 N qubits (strong scaling, the default: the metric is quoted
 "at n=30 (1/2/4/8 B200)"); ``--weak`` keeps 2^30 amplitudes per GPU instead (n = 33 on 8 GPUs).
 
+The K timed layers are applied the way the reference's ``run()`` applies them: one call per dt step of
+``trotter_per_step`` = 5 layers (its default, phase/xy_kuramoto.py:54-70) -- K // 5 calls of five layers plus K % 5
+single-layer calls; ``steps`` counts layers.  The call size changes nothing on one GPU (cyclic pass program); a sharded
+state restores its sharding once per call.
+
 Printed JSON (one line, rank 0):
   value / ms_per_step  device-timed (CUDA events on the engine's stream) steps with the state
                        resident in HBM; max over ranks.
@@ -215,6 +220,9 @@ def cpu_baseline_sample(n_target: int, gates: int = 24):
               f"n={st.n} complex128 state (C/OpenMP oracle port, {st.threads} threads), scaled by {len(st.pairs)}/{gates}"
               + ("" if st.n == n_target else f" and to n={n_target} by pairs*2^n (host memory too small for n={n_target})"))
     return layer_sec, st.threads, sample
+
+
+LAYERS_PER_CALL = 5   # the reference's default trotter_per_step (TrotterEvolutionConfig.run_steps_per_step)
 
 
 def common_config(n: int, tau: float = 0.02) -> dict:
@@ -440,6 +448,8 @@ def other_configs(device: int) -> dict:
 def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
     import torch  # device memory / streams / torch.distributed plumbing only
 
+    lpc = max(1, int(args.layers_per_call))
+
     from scpn_quantum_control_b200 import QuantumKuramotoSolver
     from scpn_quantum_control_b200.engine import XYKEngine, device_count
 
@@ -476,9 +486,24 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
     check = parity_check(eng, n, w, world, rank, device, tau, c64) if not args.no_check else None
     if check is not None:
         eng.set_problem(K, w)   # the matching check re-parameterised the engine
+    # One timed call = one dt step of the reference's run(): trotter_per_step = 5 first-order layers (its default,
+    # phase/xy_kuramoto.py:54-70, run_steps_per_step) -- a step of the metric stays ONE layer, `steps` layers are applied in steps // 5 calls of five
+    # layers plus steps % 5 single-layer calls.  On one GPU the call size changes nothing (the pass program is cyclic); a
+    # sharded state pays the exchange that restores its sharding once per call.
+    def run_layers(count: int) -> None:
+        full, rem = divmod(count, lpc)
+        for _ in range(full):
+            eng.apply_layers(lpc * tau, 1, lpc)
+        for _ in range(rem):
+            eng.apply_layers(tau, 1, 1)
+
     eng.init_product_state()
-    for _ in range(max(args.warmup, 3)):
-        eng.apply_layers(tau, 1, 1)
+    warm_layers = max(args.warmup, 3)
+    if args.steps >= lpc:
+        warm_layers = max(warm_layers, lpc)          # the five-layer program is compiled and warm
+    if args.steps % lpc and warm_layers % lpc == 0:
+        warm_layers += 1                                          # ... and so is the single-layer program
+    run_layers(warm_layers)
     raw.synchronize()
     raw.enable_timing(True)
     st0 = eng.stats()
@@ -490,8 +515,7 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
     torch.cuda.synchronize(device)
     with ClockSampler(device) as clocks:
         ev0.record(stream)
-        for _ in range(args.steps):
-            eng.apply_layers(tau, 1, 1)
+        run_layers(args.steps)
         ev1.record(stream)
         ev1.synchronize()
         torch.cuda.synchronize(device)
@@ -511,7 +535,8 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
     pass_ms = (st1["pass_kernel_ms"] - st0["pass_kernel_ms"]) / max(1, st1["pass_kernel_timed"] - st0["pass_kernel_timed"])
     peer_n = st1["peer_passes"] - st0["peer_passes"]
     peer_ms = (st1["peer_pass_ms"] - st0["peer_pass_ms"]) / max(1, peer_n)
-    rounds = st1["last_rounds"]
+    rounds = st1["last_rounds"]                                     # rounds of the last call ...
+    last_call_layers = 1 if args.steps % lpc else lpc   # ... which applied this many layers
     exchange_log = list(getattr(eng, "exchange_log", []))
     eng.close()
 
@@ -553,7 +578,11 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
                  + ("" if world == 1 else f", sharded by the top {gbits} physical qubits over {world} GPUs; qubit exchanges are fused into "
                     "the preceding tile pass as peer stores over NVLink (CUDA IPC mapped buffers), NCCL all-to-all as fallback"),
         "l2_policy": "state (16 GiB per GPU) >> L2 (126 MB): every pass streams from HBM, no flush needed",
-        "passes_per_layer": passes / args.steps, "rounds_per_layer": rounds, "sweeps_per_layer": sweeps / args.steps,
+        "passes_per_layer": passes / args.steps, "rounds_per_layer": rounds / last_call_layers, "sweeps_per_layer": sweeps / args.steps,
+        "layers_per_call": lpc,
+        "calls": f"{args.steps // lpc} x apply_layers({lpc} tau, order 1, reps {lpc})"
+                 + (f" + {args.steps % lpc} x apply_layers(tau, 1, 1)" if args.steps % lpc else "")
+                 + ": one call = one dt step of the reference's run() (trotter_per_step = 5, its default); a step of the metric is one layer",
     }
     if world > 1:
         peer_bytes = 16.0 * 2.0 ** n_shard * (world - 1) / world   # leaves this GPU per fused exchange
@@ -570,7 +599,7 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
         layer_sec, threads, sample = cpu_baseline_sample(n)
         cpu = {"value": 1.0 / layer_sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
     line = {
-        "metric": metric_name(n, args.weak), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": metric_name(n, args.weak), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm_layers,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f64" if not c64 else "f64 arithmetic on complex64 storage", "data": "synthetic",
         "config": common_config(n, tau) if not c64 else dict(common_config(n, tau), workload=f"n={n} all-to-all XY Trotter layer (first order), "
@@ -617,6 +646,8 @@ def main() -> None:
     ap.add_argument("--n", type=int, default=BASE_N, help="qubits per GPU (default: the headline n=30)")
     ap.add_argument("--dtype", default="complex128", choices=["complex128", "complex64"],
                     help="state storage (complex64: 8-byte amplitudes in HBM, FP64 arithmetic on chip; one GPU only)")
+    ap.add_argument("--layers-per-call", type=int, default=LAYERS_PER_CALL,
+                    help="layers applied per engine call in the timed loop (default: the reference's trotter_per_step = 5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check block")
     ap.add_argument("--no-other", action="store_true", help="skip the other BASELINE configs (N=1)")
