@@ -358,7 +358,7 @@ def parity_check(eng, n: int, w: np.ndarray, world: int, rank: int, device: int,
         small = ShardedXYKEngine(ns, device=device)
         small.set_problem(Ks, ws)
         rows = []
-        for order, reps in ((1, 2), (2, 1)):
+        for order, reps in ((1, 2), (2, 1), (1, LAYERS_PER_CALL)):   # the last one: the call shape of the timed loop
             small.init_product_state()
             small.apply_layers(0.1, order, reps)
             R, _ = small.order_parameter()

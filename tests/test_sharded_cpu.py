@@ -134,3 +134,24 @@ def test_random_sharded_programs():
         for op in prog["ops"]:
             if op["kind"] == "local":
                 check_plan(op["plan"])
+
+
+@pytest.mark.parametrize("n,g", [(14, 1), (15, 2), (16, 3)])
+def test_five_layer_sharded_call_matches_reference_order(n, g):
+    """one call of five first-order layers (a dt step of the reference's run(), trotter_per_step = 5) with fused
+    exchanges and the restoring exchange at its end: the program shape bench.py times on sharded states"""
+    K, w = oc.random_problem(n, 1500 + n + g)
+    Kc, wc = oc.canonicalise(n, K, w)
+    prog = plan_describe(Kc, wc, 0.1, 1, 5, n_local=n - g, peer_exchange=True, restore_sharding=True)
+    z, p = oc.term_list(Kc, wc)
+    psi0 = oc.initial_state(wc)
+    ref = oc.evolve_product_formula(psi0.copy(), z, p, 0.1, 5, 1)
+    got, perm, n_ex, n_fused = simulate_sharded(prog, n, n - g, psi0, wc)
+    assert [perm[q] for q in range(n - g, n)] == list(range(n - g, n)), "sharded qubits did not return to their rank bits"
+    inv = [0] * n
+    for q in range(n):
+        inv[perm[q]] = q
+    back = permute_bits(got, n, inv)
+    assert 1.0 - oc.fidelity(back, ref) < 1e-12
+    assert np.abs(back - ref).max() < 1e-12
+    assert n_ex + n_fused < 15, "five layers in one call need fewer exchanges than five single-layer calls (3 each)"
