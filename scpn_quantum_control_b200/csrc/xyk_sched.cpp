@@ -17,6 +17,9 @@
 #include <map>
 #include <mutex>
 #include <sstream>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "xyk_internal.h"
@@ -1519,11 +1522,31 @@ std::string plan_stages_to_json(int nq, const std::vector<Segment>& segs, const 
 Plan compile_plan(int nq, const std::vector<Segment>& segs, const SchedConfig& cfg) {
     std::lock_guard<std::mutex> memo_lock(g_memo_mutex);
     PlanCompiler pc(nq, segs, cfg);
+#ifdef XYK_EXPERIMENTS
+    static const bool timing = std::getenv("XYK_SCHED_TIMING") != nullptr;   // development build: stage times on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = now();
+    pc.prepare();
+    pc.choose_tiles();
+    const auto t1 = now();
+    pc.search_rounds();
+    const auto t2 = now();
+    pc.assign_layouts();
+    pc.emit_passes();
+    const auto t3 = now();
+    if (timing)
+        std::fprintf(stderr, "compile_plan nq=%d gates=%d passes=%zu: tiles %.1f ms, rounds %.1f ms, layouts+emit %.1f ms\n", nq, pc.plan.total_gates,
+                     pc.plan.passes.size(), ms(t0, t1), ms(t1, t2), ms(t2, t3));
+#else
     pc.prepare();
     pc.choose_tiles();
     pc.search_rounds();
     pc.assign_layouts();
     pc.emit_passes();
+#endif
     return std::move(pc.plan);
 }
 
