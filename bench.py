@@ -599,7 +599,7 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
         layer_sec, threads, sample = cpu_baseline_sample(n)
         cpu = {"value": 1.0 / layer_sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
     line = {
-        "metric": metric_name(n, args.weak), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm_layers,
+        "metric": metric_name(n, args.weak), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm_layers, "warmup_requested": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
         "dtype": "f64" if not c64 else "f64 arithmetic on complex64 storage", "data": "synthetic",
         "config": common_config(n, tau) if not c64 else dict(common_config(n, tau), workload=f"n={n} all-to-all XY Trotter layer (first order), "
