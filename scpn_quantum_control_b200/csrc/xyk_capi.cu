@@ -1521,8 +1521,35 @@ int xyk_correlation_matrix_xy(xyk_handle h, double* C) {
 int xyk_energy(xyk_handle h, double* E) {
     if (!h || !E) return XYK_ERR_INVALID;
     XYK_CHECK(h, h->have_problem, XYK_ERR_STATE, "no problem set");
-    XYK_CHECK(h, h->zz_delta == 0.0, XYK_ERR_UNSUPPORTED, "energy of the XXZ model (ZZ correlations) is not implemented");
     const int n = h->n;
+    double e_zz = 0.0;   // XXZ: -sum K_ij delta <Z_i Z_j>, one sweep over the diagonal quadratic form
+    if (h->zz_delta != 0.0 && !h->pairs.empty()) {
+        XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "XXZ energy of a sharded state is not supported");
+        XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+        XYK_CUDA(h, cudaSetDevice(h->device));
+        ZZSpec S{};
+        S.nbits = h->n;
+        S.nlocal = h->nlocal;
+        S.rank = h->rank;
+        S.LB = std::min(h->nlocal, 12);
+        S.t = 1.0;
+        for (int q = 0; q < h->n; ++q) S.log_of_bit[h->perm[q]] = q;
+        double* qtab = reinterpret_cast<double*>(h->d_zztab);   // 4096 doubles fit the 4096 double2 entries
+        zz_low_qtable_kernel<<<16, 256, 0, h->stream>>>(qtab, h->d_J, h->n, S);
+        const uint64_t nblk = 1ull << (h->nlocal - S.LB);
+        const int grid = (int)std::min<uint64_t>(nblk, (uint64_t)kRedBlocks);
+        if (h->dtype == 0)
+            zz_energy_kernel<double><<<grid, 256, 0, h->stream>>>((const double2*)h->buf[h->cur], qtab, h->d_J, h->n, S, h->d_partial);
+        else
+            zz_energy_kernel<float><<<grid, 256, 0, h->stream>>>((const float2*)h->buf[h->cur], qtab, h->d_J, h->n, S, h->d_partial);
+        reduce_partials_kernel<<<1, 128, 0, h->stream>>>(h->d_partial, grid, 1, h->d_out);
+        h->stats.kernel_launches += 3;
+        h->stats.state_sweeps += 1;
+        XYK_CUDA(h, cudaGetLastError());
+        XYK_CUDA(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        XYK_CUDA(h, cudaStreamSynchronize(h->stream));
+        e_zz = -h->h_out[0];   // d_J holds K_ij * delta: the term is -K_ij delta Z_i Z_j
+    }
     std::vector<double> C((size_t)n * n), z(n);
     int rc = xyk_correlation_matrix_xy(h, C.data());
     if (rc) return rc;
@@ -1532,7 +1559,7 @@ int xyk_energy(xyk_handle h, double* E) {
     for (int i = 0; i < n; ++i)
         for (int j = i + 1; j < n; ++j) e -= h->Ksym[(size_t)i * n + j] * C[(size_t)i * n + j];
     for (int i = 0; i < n; ++i) e -= h->omega[i] * z[i];
-    *E = e;
+    *E = e + e_zz;
     return XYK_OK;
 }
 

@@ -290,6 +290,80 @@ __global__ void __launch_bounds__(256) zz_diag_kernel(typename cplx<real>::type*
     }
 }
 
+// <sum_{a<b} J_ab Z_a Z_b> = sum_k |psi_k|^2 q(k) with the quadratic form q of zz_diag_kernel (same Lo / Hi split: the low-bit
+// part from a table of q values, the linear part from two 64-entry tables per k_hi): the ZZ part of the XXZ energy in ONE
+// sweep instead of one sweep per pair.  partial[blockIdx.x] = this block's sum.
+__global__ void zz_low_qtable_kernel(double* __restrict__ qtab, const double* __restrict__ J, int ldJ, const __grid_constant__ ZZSpec S) {
+    const int cnt = 1 << S.LB;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < cnt; v += gridDim.x * blockDim.x) {
+        double q = 0.0;
+        for (int a = 0; a < S.LB; ++a)
+            for (int b = a + 1; b < S.LB; ++b) {
+                const double jab = J[S.log_of_bit[a] * ldJ + S.log_of_bit[b]];
+                q += (((v >> a) ^ (v >> b)) & 1) ? -jab : jab;
+            }
+        qtab[v] = q;
+    }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) zz_energy_kernel(const typename cplx<real>::type* __restrict__ psi, const double* __restrict__ qtab,
+                                                        const double* __restrict__ J, int ldJ, const __grid_constant__ ZZSpec S,
+                                                        double* __restrict__ partial) {
+    __shared__ double f[16];
+    __shared__ double qhi;
+    __shared__ double la[64], lb[64];
+    __shared__ double red[32];
+    const int LB = S.LB, nhi = S.nbits - LB;
+    const uint64_t nblk = 1ull << (S.nlocal - LB);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[1] = {0.0};
+    for (uint64_t kh = blockIdx.x; kh < nblk; kh += gridDim.x) {
+        const uint64_t hibits = kh | ((uint64_t)S.rank << (S.nlocal - LB));
+        if (warp == 0) {
+            if (lane < LB) {
+                double a = 0.0;
+                for (int b = 0; b < nhi; ++b) {
+                    const double jab = J[S.log_of_bit[lane] * ldJ + S.log_of_bit[LB + b]];
+                    a += ((hibits >> b) & 1) ? -jab : jab;
+                }
+                f[lane] = a;
+            }
+        } else if (warp == 1) {
+            double a = 0.0;
+            for (int idx = lane; idx < nhi * nhi; idx += 32) {
+                const int x = idx / nhi, y = idx - x * nhi;
+                if (x < y) {
+                    const double jab = J[S.log_of_bit[LB + x] * ldJ + S.log_of_bit[LB + y]];
+                    a += (((hibits >> x) ^ (hibits >> y)) & 1) ? -jab : jab;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) qhi = a;
+        }
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int v = threadIdx.x & 63, half = threadIdx.x >> 6;
+            double ph = half ? qhi : 0.0;
+            for (int b = 0; b < 6; ++b) {
+                const int a = half * 6 + b;
+                if (a < LB) ph += ((v >> b) & 1) ? -f[a] : f[a];
+            }
+            (half ? lb : la)[v] = ph;
+        }
+        __syncthreads();
+        const typename cplx<real>::type* base = psi + (kh << LB);
+        for (int x = threadIdx.x; x < (1 << LB); x += 256) {
+            const typename cplx<real>::type v = base[x];
+            const double pr = (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+            acc[0] += pr * (__ldg(&qtab[x]) + la[x & 63] + lb[x >> 6]);
+        }
+        __syncthreads();
+    }
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc[0];
+}
+
 // ---- exact step by Chebyshev expansion on a fused H.phi sweep (reference twin: hardware/classical.py:201-208, expm_multiply) ----
 // H = -sum_{i<j} K_ij (XX + YY + delta ZZ) - sum_i w_i Z_i acts on amplitude k as
 //   (H phi)_k = d(k) phi_k - 2 sum_{(a,b): bits differ} K_ab phi_{k ^ (m_a | m_b)},   d(k) = -sum_a w_a z_a - delta sum K_ab z_a z_b

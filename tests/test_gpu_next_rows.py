@@ -401,3 +401,27 @@ def test_complex64_next_row_kernels():
         eng.init_product_state()
         with pytest.raises(RuntimeError):
             eng.exact_step(0.1)   # the Chebyshev step needs a complex128 state
+
+
+@pytest.mark.parametrize("n,engine,dtype", [(7, "simple", "complex128"), (13, "tiled", "complex128"), (16, "tiled", "complex128"),
+                                           (13, "tiled", "complex64")])
+def test_xxz_energy_vs_oracle(n, engine, dtype):
+    """<H> of the XXZ model: XY correlations + <Z> + the ZZ part from ONE sweep over the diagonal quadratic form
+    (zz_energy_kernel), on a permuted layout, against <psi|H|psi> of the oracle's sparse XXZ Hamiltonian"""
+    K, w = oc.random_problem(n, 3100 + n)
+    Kc, wc = oc.canonicalise(n, K, w)
+    delta = 0.8
+    with XYKEngine(n, dtype=dtype) as eng:
+        eng.set_problem(Kc, wc, delta)
+        eng.set_engine(engine)
+        eng.init_product_state()
+        e0 = eng.energy()
+        eng.apply_layers(0.06, 2, 2)
+        e1 = eng.energy()
+        psi = eng.get_state().astype(np.complex128)
+    H = on.hamiltonian_sparse_xxz(Kc, wc, delta)
+    psi0 = oc.initial_state(wc)
+    tol = 1e-9 if dtype == "complex128" else 1e-3
+    assert abs(e0 - float(np.real(np.vdot(psi0, H @ psi0)))) < tol
+    assert abs(e1 - float(np.real(np.vdot(psi, H @ psi))) / float(np.real(np.vdot(psi, psi)))) < tol
+    assert abs(e1 - e0) < 0.05 * max(1.0, abs(e0))   # a second-order step conserves the energy up to its splitting error
