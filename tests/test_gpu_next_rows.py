@@ -425,3 +425,41 @@ def test_xxz_energy_vs_oracle(n, engine, dtype):
     assert abs(e0 - float(np.real(np.vdot(psi0, H @ psi0)))) < tol
     assert abs(e1 - float(np.real(np.vdot(psi, H @ psi))) / float(np.real(np.vdot(psi, psi)))) < tol
     assert abs(e1 - e0) < 0.05 * max(1.0, abs(e0))   # a second-order step conserves the energy up to its splitting error
+
+
+def test_next_rows_vs_committed_golden_vectors():
+    """the GPU path against tests/golden/next_rows_vectors.json (feedback history, XXZ traces, Floquet drive)"""
+    import json
+    import os
+
+    from scpn_quantum_control_b200 import QuantumKuramotoSolver
+    from scpn_quantum_control_b200.floquet_kuramoto import floquet_evolve
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next_rows_vectors.json")))
+    fb = g["feedback_n4_seed123_trotter_order1"]
+    ctl = RealtimeSyncFeedbackController(oc.paper27_K(16)[:4, :4] * 2.0, oc.OMEGA_N_16[:4], RealtimeFeedbackConfig(**fb["config"]),
+                                         trotter_order=1, evolution="trotter")
+    hist = ctl.run(fb["n_steps"], seed=fb["seed"])
+    ctl.close()
+    for got, want in zip(hist, fb["history"]):
+        assert got.action == want["action"] and dict(got.readout_counts) == want["readout_counts"]
+        assert abs(got.r_statevector - want["r_statevector"]) < R_TOL
+        assert got.r_live == pytest.approx(want["r_live"], abs=1e-12)
+        assert got.next_coupling_scale == pytest.approx(want["next_coupling_scale"], abs=1e-12)
+    x = g["xxz_n6"]
+    K, w = oc.random_problem(6, 11)
+    for order in (1, 2):
+        s = QuantumKuramotoSolver(6, K, w, anisotropy_delta=x["delta"], evolution="trotter", trotter_order=order)
+        R = s.run(x["t_max"], x["dt"], 4)["R"]
+        s.close()
+        assert np.abs(R - np.array(x[f"R_trotter_order{order}_4_per_step"])).max() < R_TOL
+    s = QuantumKuramotoSolver(6, K, w, anisotropy_delta=x["delta"])
+    R = s.run(x["t_max"], x["dt"])["R"]
+    s.close()
+    assert np.abs(R - np.array(x["R_exact"])).max() < R_TOL
+    f = g["floquet_n4"]
+    Kp = oc.paper27_K(16)[:4, :4]
+    fl = floquet_evolve(Kp / Kp.max(), oc.OMEGA_N_16[:4], f["K_base"], f["drive_amplitude"], f["drive_frequency"], f["n_periods"],
+                        f["steps_per_period"])
+    assert np.abs(fl.R_values - np.array(f["R_values"])).max() < 1e-8
+    assert np.allclose(fl.drive_signal, f["drive_signal"], rtol=0, atol=1e-14)

@@ -101,3 +101,34 @@ def test_solver_rejects_bad_next_row_arguments():
     with pytest.raises(ValueError, match="evolution='chebyshev' needs a single-device complex128 state"):
         QuantumKuramotoSolver(4, K, w, evolution="chebyshev", dtype="complex64")
     assert QuantumKuramotoSolver(4, K, w, anisotropy_delta=1e-16).anisotropy_delta == 0.0  # below the reference's sparsity threshold
+
+
+def _next_rows_goldens():
+    import json
+    import os
+
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "next_rows_vectors.json")))
+
+
+def test_next_rows_oracle_reproduces_the_committed_vectors():
+    g = _next_rows_goldens()
+    fb = g["feedback_n4_seed123_trotter_order1"]
+    K, w = oc.paper27_K(16)[:4, :4] * 2.0, oc.OMEGA_N_16[:4]
+    rows, _ = on.feedback_run(K, w, fb["n_steps"], fb["seed"], order=1, mode="T", **fb["config"])
+    for got, want in zip(rows, fb["history"]):
+        assert got["action"] == want["action"] and got["readout_counts"] == want["readout_counts"]
+        for key in ("r_live", "r_statevector", "psi_statevector", "error", "next_coupling_scale", "correction_angle"):
+            assert got[key] == pytest.approx(want[key], abs=1e-13)
+    x = g["xxz_n6"]
+    K, w = oc.random_problem(6, 11)
+    for order in (1, 2):
+        _, R = on.run_xxz(6, K, w, x["delta"], x["t_max"], x["dt"], 4, order=order, mode="T")
+        assert np.abs(R - np.array(x[f"R_trotter_order{order}_4_per_step"])).max() < 1e-13
+    _, RE = on.run_xxz(6, K, w, x["delta"], x["t_max"], x["dt"], mode="E")
+    assert np.abs(RE - np.array(x["R_exact"])).max() < 1e-12
+    f = g["floquet_n4"]
+    Kp = oc.paper27_K(16)[:4, :4]
+    fl = on.floquet_evolve(Kp / Kp.max(), oc.OMEGA_N_16[:4], f["K_base"], f["drive_amplitude"], f["drive_frequency"], f["n_periods"],
+                           f["steps_per_period"])
+    assert np.abs(fl["R_values"] - np.array(f["R_values"])).max() < 1e-12
+    assert fl["subharmonic_ratio"] == pytest.approx(f["subharmonic_ratio"], rel=1e-9)
