@@ -643,7 +643,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=BASE_N, help="qubits per GPU (default: the headline n=30)")
+    ap.add_argument("--n", "--qubits", dest="n", type=int, default=BASE_N,
+                    help="total qubits (with --weak: qubits per GPU); default: the headline n=30.  Under torchrun use --qubits "
+                         "(torchrun's own parser claims the prefix --n)")
     ap.add_argument("--dtype", default="complex128", choices=["complex128", "complex64"],
                     help="state storage (complex64: 8-byte amplitudes in HBM, FP64 arithmetic on chip; one GPU only)")
     ap.add_argument("--layers-per-call", type=int, default=LAYERS_PER_CALL,
