@@ -20,6 +20,10 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
+#include <thread>
+#include <set>
+#include <exception>
 #include <stdexcept>
 
 #include "xyk_internal.h"
@@ -692,7 +696,9 @@ struct PlanCompiler {
             if (popc(both & ~blocked) < 2) break;
         }
     };
-    int cur_unb_kind = 0;  // left-group size of the unbalanced split rounds the searches may use right now (0: none)
+    // (thread-local: the passes of a program are decomposed by several host threads, each with its own search state)
+    static thread_local int cur_unb_kind;  // left-group size of the unbalanced split rounds the searches may use right now (0: none)
+    cur_unb_kind = 0;
     auto search_split = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cdone, bool reverse_scan,
                             uint64_t limit_mask, int limit, uint64_t prefer, RawRound& best) {
         std::vector<int> tq;
@@ -787,7 +793,8 @@ struct PlanCompiler {
     };
     // the better of a complex round and (when allowed) a split round; ties go to the complex round
     // (half as many shared-memory instructions for the same bytes)
-    bool allow_split = can_split;
+    static thread_local bool allow_split;
+    allow_split = can_split;
     auto search_round = [&](const RawPass& rp, const std::vector<Gate>& g, const std::vector<char>& cdone,
                             bool reverse_scan, uint64_t limit_mask, int limit, uint64_t prefer, RawRound& best) {
         search_complex(rp, g, cdone, reverse_scan, limit_mask, limit, prefer, best);
@@ -930,28 +937,27 @@ struct PlanCompiler {
         for (int k : rp.gate_idx) os << g[k].i << ',' << g[k].j << ',' << (g[k].reverse ? 1 : 0) << ',' << (g[k].sweep - s0) << ';';
         return os.str();
     };
-    // (a) last rounds
-    for (int p = 0; p < P; ++p) {
+    // The passes of a program are independent here (a pass only looks at its own gates and at the neighbouring TILES):
+    // those whose decomposition is not memoised yet -- one per distinct key -- are searched by a small pool of host threads,
+    // the others are filled in from the memo afterwards.  The result does not depend on the thread count or timing: a memo hit
+    // returns exactly what the search computes.
+    std::vector<std::string> keys(P);
+    for (int p = 0; p < P; ++p) keys[p] = memo_key(p);
+    std::vector<int> todo;
+    std::vector<char> computed(P, 0);
+    {
+        std::set<std::string> seen;
+        for (int p = 0; p < P; ++p)
+            if (memo.find(keys[p]) == memo.end() && seen.insert(keys[p]).second) {
+                todo.push_back(p);
+                computed[p] = 1;
+            }
+    }
+    auto decompose_pass = [&](int p) {
+        cur_unb_kind = 0;
+        allow_split = can_split;
         const RawPass& rp = raw[p];
         const std::vector<Gate>& g = sg[rp.seg];
-        const std::string key = memo_key(p);
-        auto it = memo.find(key);
-        if (it != memo.end()) {
-            last_round[p] = it->second.last;
-            rr[p] = it->second.front;
-            rlast[p] = last_round[p].rmask;
-            for (int c : last_round[p].cidx) cdone[p][c] = 1;
-            for (auto& r : rr[p])
-                for (int c : r.cidx) cdone[p][c] = 1;
-            if (rr[p].empty()) {
-                single_round[p] = 1;
-                rfirst[p] = rlast[p];
-            } else {
-                rfirst[p] = rr[p][0].rmask;
-                first_round[p] = rr[p][0];
-            }
-            continue;
-        }
         // one decomposition per admissible kind of unbalanced split round (none / 2 | 4 / 1 | 5: a pass never mixes the
         // two, each lives in its own kernel instantiation); the fewest rounds win, ties go to the leaner kernel
         auto decompose = [&]() {
@@ -1062,7 +1068,46 @@ struct PlanCompiler {
             rfirst[p] = rr[p][0].rmask;
             first_round[p] = rr[p][0];
         }
-        memo[key] = RoundsMemo{last_round[p], rr[p]};
+    };
+    {
+        unsigned nthreads = std::min<unsigned>({std::max(1u, std::thread::hardware_concurrency()), 8u, (unsigned)todo.size()});
+        if (nthreads <= 1) {
+            for (int p : todo) decompose_pass(p);
+        } else {
+            std::atomic<size_t> next_item{0};
+            std::vector<std::exception_ptr> errors(nthreads);
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nthreads; ++t)
+                pool.emplace_back([&, t]() {
+                    try {
+                        for (size_t k = next_item++; k < todo.size(); k = next_item++) decompose_pass(todo[k]);
+                    } catch (...) {
+                        errors[t] = std::current_exception();
+                    }
+                });
+            for (auto& th : pool) th.join();
+            for (auto& e : errors)
+                if (e) std::rethrow_exception(e);
+        }
+    }
+    for (int p : todo) memo[keys[p]] = RoundsMemo{last_round[p], rr[p]};
+    for (int p = 0; p < P; ++p) {
+        if (computed[p]) continue;
+        const auto it = memo.find(keys[p]);
+        if (it == memo.end()) throw std::runtime_error("compile_plan: round memo lost an entry");
+        last_round[p] = it->second.last;
+        rr[p] = it->second.front;
+        rlast[p] = last_round[p].rmask;
+        for (int c : last_round[p].cidx) cdone[p][c] = 1;
+        for (auto& r : rr[p])
+            for (int c : r.cidx) cdone[p][c] = 1;
+        if (rr[p].empty()) {
+            single_round[p] = 1;
+            rfirst[p] = rlast[p];
+        } else {
+            rfirst[p] = rr[p][0].rmask;
+            first_round[p] = rr[p][0];
+        }
     }
     for (int p = 0; p < P; ++p) rr[p].push_back(last_round[p]);
     }
