@@ -577,7 +577,7 @@ def run_gpu_arm(args, rank: int, world: int, local_rank: int) -> None:
         "state": f"{amp_bytes * 2 ** n_shard / 2 ** 30:.2f} GiB shard per GPU"
                  + ("" if world == 1 else f", sharded by the top {gbits} physical qubits over {world} GPUs; qubit exchanges are fused into "
                     "the preceding tile pass as peer stores over NVLink (CUDA IPC mapped buffers), NCCL all-to-all as fallback"),
-        "l2_policy": "state (16 GiB per GPU) >> L2 (126 MB): every pass streams from HBM, no flush needed",
+        "l2_policy": f"state shard ({amp_bytes * 2 ** n_shard / 2 ** 30:.0f} GiB per GPU) >> L2 (126 MB): every pass streams from HBM, no flush needed",
         "passes_per_layer": passes / args.steps, "rounds_per_layer": rounds / last_call_layers, "sweeps_per_layer": sweeps / args.steps,
         "layers_per_call": lpc,
         "calls": f"{args.steps // lpc} x apply_layers({lpc} tau, order 1, reps {lpc})"
