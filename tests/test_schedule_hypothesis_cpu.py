@@ -32,7 +32,7 @@ def problems(draw):
     return n, K, w, delta, order, reps
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@settings(max_examples=60, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(problems())
 def test_compiled_program_is_the_reference_gate_order(problem):
     n, K, w, delta, order, reps = problem
