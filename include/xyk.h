@@ -155,6 +155,16 @@ int xyk_apply_ry(xyk_handle h, const double *angles);
  * route to what Statevector.evolve returns under the reference's pinned Qiskit (Mode E).  Single-GPU, complex128. */
 int xyk_exact_step(xyk_handle h, double dt, double tol, int *terms_used);
 
+/* Quantum-jump (Monte Carlo wave function) building blocks on the live state; single-GPU handles.
+ * Replaces: the non-Hermitian part of H_eff = H - (i/2) sum L^dagger L and the jump operators of mcwf_trajectory
+ * (phase/tensor_jump.py:157-206).  For the reference's operators -- sqrt(gamma_amp) |1><0| and sqrt(gamma_deph / 2) Z per
+ * qubit -- sum L^dagger L is diagonal in the computational basis and commutes with H (H conserves the number of ones), so
+ * exp(-i H_eff dt) = exp(-i H dt) followed by a real factor per amplitude that depends on its bit counts only:
+ *   xyk_apply_occupation_decay: psi_k *= scale * exp(-rate_zero * #zero bits(k) - rate_one * #one bits(k));
+ *   xyk_apply_jump: kind 0: psi <- |1><0|_q psi (the reference's "-" matrix), kind 1: psi <- Z_q psi. */
+int xyk_apply_occupation_decay(xyk_handle h, double rate_zero, double rate_one, double scale);
+int xyk_apply_jump(xyk_handle h, int qubit, int kind);
+
 /* The whole run() loop on the device: init, R[0], then for each step_sizes[s]: evolve, R[s+1].
  * Replaces: QuantumKuramotoSolver.run hot loop (xy_kuramoto.py:236-248). Single GPU only. */
 int xyk_run(xyk_handle h, const double *step_sizes, int m, int reps, int order, double *R_out);

@@ -10,6 +10,8 @@ NumPy restatements (reference paths relative to /root/reference):
                                :402-423 (binomial axis sample, multinomial read-out)
 * XXZ term list                src/scpn_quantum_control/bridge/knm_hamiltonian.py:172-206 (delta != 0: per pair
                                XX, YY, ZZ with coefficients -K, -K, -K*delta)
+* MCWF trajectories            src/scpn_quantum_control/phase/tensor_jump.py:81-291 (sparse H_eff, Kronecker-order jump
+                               operators, jump lottery)
 * Floquet drive                src/scpn_quantum_control/phase/floquet_kuramoto.py:67-221 (K(t) = K_base (1 + A cos(Omega t))
                                K_topology sampled at the midpoint of every step, exact exp(-i H dt) per step from |+>^n)
 
@@ -268,3 +270,82 @@ def floquet_evolve(K_topology, omega, K_base, drive_amplitude, drive_frequency, 
         drive[s + 1] = K_t
     out = dict(times=times, R_values=R, drive_signal=drive, subharmonic_ratio=subharmonic_ratio(R[1:], drive_frequency, dt))
     return (out, psi) if return_state else out
+
+
+# --------------------------------------------------------------------------------------
+# Monte Carlo wave function trajectories (phase/tensor_jump.py:81-291)
+# --------------------------------------------------------------------------------------
+def _kron_single(op2, qubit, n):
+    """Sparse single-qubit operator in the reference's Kronecker order: oscillator 0 is the FIRST factor (:81-93)."""
+    import scipy.sparse as sp
+
+    out = sp.identity(1, dtype=np.complex128, format="csr")
+    ident = sp.identity(2, dtype=np.complex128, format="csr")
+    for i in range(n):
+        out = sp.kron(out, sp.csr_matrix(op2) if i == qubit else ident, format="csr")
+    return out
+
+
+def mcwf_order_parameter(psi, n):
+    """_order_param_vec (:274-291): |sum_i (<X_i> + i <Y_i>)| / n with oscillator i on index bit n-1-i."""
+    ex, ey = oc.xy_expectations(psi, n)   # a sum over all qubits does not care about the labelling
+    return float(abs(complex(ex.sum(), ey.sum()) / n))
+
+
+def mcwf_trajectory(K, omega, gamma_amp=0.05, gamma_deph=0.0, t_max=1.0, dt=0.05, seed=None):
+    """Literal restatement of mcwf_trajectory (:120-219): H = the little-endian XY Hamiltonian matrix
+    (knm_to_sparse_matrix = SparsePauliOp.to_matrix), state / jump operators in Kronecker (big-endian) order, every step
+    expm_multiply(-i H_eff dt) with H_eff = H - (i/2) sum L^dagger L, then the jump lottery in the reference's generator
+    call order."""
+    from scipy import sparse
+    from scipy.sparse.linalg import expm_multiply
+
+    K = np.asarray(K, dtype=np.float64)
+    omega = np.asarray(omega, dtype=np.float64)
+    n = K.shape[0]
+    dim = 1 << n
+    rng = np.random.default_rng(seed)
+    psi = np.array([1.0 + 0.0j])
+    for w in omega:
+        a = float(w) % (2 * np.pi)
+        psi = np.kron(psi, np.array([np.cos(a / 2), np.sin(a / 2)], dtype=np.complex128))
+    if t_max == 0.0:
+        return {"times": np.array([0.0]), "R": np.array([mcwf_order_parameter(psi, n)]), "psi_final": psi, "n_jumps": 0}
+    Ks = (K + K.T) / 2.0
+    H = oc.hamiltonian_sparse(Ks, omega).astype(np.complex128)
+    L_ops = []
+    for i in range(n):
+        if gamma_amp > 0:
+            L_ops.append(np.sqrt(gamma_amp) * _kron_single(np.array([[0, 0], [1, 0]], dtype=np.complex128), i, n))
+        if gamma_deph > 0:
+            L_ops.append(np.sqrt(gamma_deph / 2) * _kron_single(np.array([[1, 0], [0, -1]], dtype=np.complex128), i, n))
+    anti = sparse.csr_matrix((dim, dim), dtype=np.complex128)
+    for L in L_ops:
+        anti = anti + (L.getH() @ L)
+    H_eff = (H - 0.5j * anti).tocsc()
+    n_steps = max(1, int(np.ceil(t_max / dt)))
+    times = np.linspace(0, t_max, n_steps + 1)
+    R = np.zeros(n_steps + 1)
+    R[0] = mcwf_order_parameter(psi, n)
+    n_jumps = 0
+    for step in range(1, n_steps + 1):
+        step_dt = float(times[step] - times[step - 1])
+        psi_new = expm_multiply(-1j * H_eff * step_dt, psi)
+        norm_sq = float(np.real(np.dot(psi_new.conj(), psi_new)))
+        dp = float(np.clip(1 - norm_sq, 0.0, 1.0))
+        r = rng.uniform()
+        if r < dp and len(L_ops) > 0:
+            probs = np.array([float(np.real(np.dot((L @ psi).conj(), L @ psi))) for L in L_ops])
+            total = probs.sum()
+            if total > 1e-15:
+                probs /= total
+                k = rng.choice(len(L_ops), p=probs)
+                psi = L_ops[k] @ psi
+                psi = psi / np.linalg.norm(psi)
+                n_jumps += 1
+            else:
+                psi = psi_new / np.sqrt(norm_sq) if norm_sq > 1e-15 else psi_new
+        else:
+            psi = psi_new / np.sqrt(norm_sq) if norm_sq > 1e-15 else psi_new
+        R[step] = mcwf_order_parameter(psi, n)
+    return {"times": times, "R": R, "psi_final": psi, "n_jumps": n_jumps}

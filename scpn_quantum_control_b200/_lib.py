@@ -76,6 +76,8 @@ PROTOTYPES = {
     "xyk_set_problem_xxz": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), c_double]),
     "xyk_exact_step": (c_int, [c_void_p, c_double, c_double, POINTER(c_int)]),
     "xyk_xy_expectations_peer": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
+    "xyk_apply_occupation_decay": (c_int, [c_void_p, c_double, c_double, c_double]),
+    "xyk_apply_jump": (c_int, [c_void_p, c_int, c_int]),
     "xyk_apply_ry": (c_int, [c_void_p, POINTER(c_double)]),
     "xyk_init_product_angles": (c_int, [c_void_p, POINTER(c_double)]),
     "xyk_run": (c_int, [c_void_p, POINTER(c_double), c_int, c_int, c_int, POINTER(c_double)]),

@@ -1563,6 +1563,59 @@ int xyk_energy(xyk_handle h, double* E) {
     return XYK_OK;
 }
 
+int xyk_apply_occupation_decay(xyk_handle h, double rate_zero, double rate_one, double scale) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "occupation decay of a sharded state is not supported");
+    XYK_CHECK(h, std::isfinite(rate_zero) && std::isfinite(rate_one) && std::isfinite(scale), XYK_ERR_INVALID, "rates and scale must be finite");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    // psi_k *= scale * exp(-rate_zero * #zeros(k) - rate_one * #ones(k)): three host-built chunk tables (real factors) through
+    // the table-apply kernel of the diagonal phase; the factor does not depend on the layout (it counts bits)
+    const int nl = h->nlocal;
+    int b1 = std::min(nl, 11), b2 = std::min(nl, 22);
+    if (nl - b2 > 11) {
+        b1 = (nl + 2) / 3;
+        b2 = b1 + (nl - b1 + 1) / 2;
+    }
+    XYK_CHECK(h, b1 <= 11 && b2 - b1 <= 11 && nl - b2 <= 11, XYK_ERR_UNSUPPORTED, "decay tables support at most 33 local qubits");
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));   // the pinned staging buffer is shared with other calls
+    std::vector<double2> tab((size_t)3 * kTabStride, make_double2(1.0, 0.0));
+    const int lo[3] = {0, b1, b2}, hi[3] = {b1, b2, nl};
+    for (int c = 0; c < 3; ++c)
+        for (int v = 0; v < (1 << (hi[c] - lo[c])); ++v) {
+            const int ones = __builtin_popcount((unsigned)v), zeros = (hi[c] - lo[c]) - ones;
+            tab[(size_t)c * kTabStride + v] = make_double2((c == 0 ? scale : 1.0) * std::exp(-rate_zero * zeros - rate_one * ones), 0.0);
+        }
+    XYK_CUDA(h, cudaMemcpy(h->d_tab, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
+    const uint64_t dim = 1ull << nl;
+    if (h->dtype == 0)
+        phase_apply_kernel<double><<<grid_for(h, dim, 256), 256, 0, h->stream>>>((double2*)h->buf[h->cur], h->d_tab, kTabStride, nl, b1, b2);
+    else
+        phase_apply_kernel<float><<<grid_for(h, dim, 256), 256, 0, h->stream>>>((float2*)h->buf[h->cur], h->d_tab, kTabStride, nl, b1, b2);
+    h->stats.kernel_launches++;
+    h->stats.state_sweeps++;
+    XYK_CUDA(h, cudaGetLastError());
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));   // d_tab is rewritten by the next phase / init call
+    return XYK_OK;
+}
+
+int xyk_apply_jump(xyk_handle h, int qubit, int kind) {
+    if (!h) return XYK_ERR_INVALID;
+    XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");
+    XYK_CHECK(h, h->world == 1, XYK_ERR_UNSUPPORTED, "jump operators on a sharded state are not supported");
+    XYK_CHECK(h, qubit >= 0 && qubit < h->n && (kind == 0 || kind == 1), XYK_ERR_INVALID, "bad qubit or jump kind");
+    XYK_CUDA(h, cudaSetDevice(h->device));
+    const uint64_t half = 1ull << (h->nlocal - 1);
+    if (h->dtype == 0)
+        jump_kernel<double><<<grid_for(h, half, 256), 256, 0, h->stream>>>((double2*)h->buf[h->cur], h->nlocal, h->perm[qubit], kind);
+    else
+        jump_kernel<float><<<grid_for(h, half, 256), 256, 0, h->stream>>>((float2*)h->buf[h->cur], h->nlocal, h->perm[qubit], kind);
+    h->stats.kernel_launches++;
+    h->stats.state_sweeps++;
+    XYK_CUDA(h, cudaGetLastError());
+    return XYK_OK;
+}
+
 int xyk_apply_ry(xyk_handle h, const double* angles) {
     if (!h || !angles) return XYK_ERR_INVALID;
     XYK_CHECK(h, h->state_valid, XYK_ERR_STATE, "state not initialised");

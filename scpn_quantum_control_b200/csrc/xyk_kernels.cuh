@@ -188,6 +188,29 @@ __global__ void __launch_bounds__(256) peer_dot_kernel(const double2* __restrict
     if (threadIdx.x == 0) partial[blockIdx.x] = make_double2(v[0], v[1]);
 }
 
+// ---- quantum-jump (MCWF) helpers: phase/tensor_jump.py:157-206 ----
+// kind 0: psi <- sigma_q psi with sigma = |1><0| on physical bit `pos` (the reference's "-" matrix [[0, 0], [1, 0]]: the
+//         amplitude with the bit clear moves to its partner with the bit set, the clear half becomes 0);
+// kind 1: psi <- Z_q psi.
+template <typename real>
+__global__ void jump_kernel(typename cplx<real>::type* __restrict__ psi, int nlocal, int pos, int kind) {
+    const uint64_t half = 1ull << (nlocal - 1);
+    const uint64_t m = 1ull << pos;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < half; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = insert_zero64(t, pos);
+        if (kind == 0) {
+            psi[k | m] = psi[k];
+            psi[k].x = (real)0;
+            psi[k].y = (real)0;
+        } else {
+            typename cplx<real>::type b = psi[k | m];
+            b.x = -b.x;
+            b.y = -b.y;
+            psi[k | m] = b;
+        }
+    }
+}
+
 // ---- XXZ anisotropy: diagonal ZZ phases (bridge/knm_hamiltonian.py:196-201, term -K_ij delta Z_i Z_j) ----
 // psi_k *= exp(+i theta z_i z_j), z = 1 - 2 bit: one pair, gate-by-gate engine (reference term order XX, YY, ZZ per pair)
 template <typename real>

@@ -99,6 +99,14 @@ class XYKEngine:
     def init_product_state(self) -> None:
         self._check(self._lib.xyk_init_product_state(self._h))
 
+    def apply_occupation_decay(self, rate_zero: float, rate_one: float = 0.0, scale: float = 1.0) -> None:
+        """psi_k *= scale * exp(-rate_zero * #zero bits(k) - rate_one * #one bits(k)) (MCWF no-jump damping, re-scaling)."""
+        self._check(self._lib.xyk_apply_occupation_decay(self._h, float(rate_zero), float(rate_one), float(scale)))
+
+    def apply_jump(self, qubit: int, kind: int) -> None:
+        """kind 0: psi <- |1><0|_q psi (the reference's "-" matrix); kind 1: psi <- Z_q psi.  Not normalised."""
+        self._check(self._lib.xyk_apply_jump(self._h, int(qubit), int(kind)))
+
     def exact_step(self, dt: float, tol: float = 1e-13) -> int:
         """psi <- exp(-i H dt) psi by Chebyshev expansion (no splitting error); returns the number of terms."""
         used = c_int()

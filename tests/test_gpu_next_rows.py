@@ -463,3 +463,53 @@ def test_next_rows_vs_committed_golden_vectors():
                         f["steps_per_period"])
     assert np.abs(fl.R_values - np.array(f["R_values"])).max() < 1e-8
     assert np.allclose(fl.drive_signal, f["drive_signal"], rtol=0, atol=1e-14)
+
+
+def test_mcwf_building_blocks_on_the_device():
+    """xyk_apply_occupation_decay and xyk_apply_jump on a permuted layout against NumPy"""
+    n = 13
+    K, w = oc.random_problem(n, 1313)
+    Kc, wc = oc.canonicalise(n, K, w)
+    with XYKEngine(n) as eng:
+        eng.set_problem(Kc, wc)
+        eng.set_engine("tiled")
+        eng.init_product_state()
+        eng.apply_layers(0.05, 1, 1)
+        ref = eng.get_state()
+        eng.apply_occupation_decay(0.3, 0.1, 0.7)
+        got = eng.get_state()
+        idx = np.arange(1 << n)
+        ones = np.array([bin(int(k)).count("1") for k in idx])
+        want = ref * (0.7 * np.exp(-0.3 * (n - ones) - 0.1 * ones))
+        assert np.abs(got - want).max() < 1e-14
+        eng.apply_jump(5, 0)
+        m = 1 << 5
+        w2 = np.zeros_like(want)
+        lower = idx[(idx & m) == 0]
+        w2[lower | m] = want[lower]
+        assert np.abs(eng.get_state() - w2).max() < 1e-14
+        eng.apply_jump(11, 1)
+        w3 = np.where(idx & (1 << 11), -w2, w2)
+        assert np.abs(eng.get_state() - w3).max() < 1e-14
+
+
+@pytest.mark.parametrize("n,gamma_amp,gamma_deph,seed", [(4, 0.6, 0.4, 7), (6, 1.5, 0.5, 11), (13, 0.8, 0.3, 2)])
+def test_mcwf_trajectory_vs_oracle(n, gamma_amp, gamma_deph, seed):
+    """mcwf_trajectory on the device (exact step + bit-count damping + jump kernels) vs the oracle's literal restatement
+    of phase/tensor_jump.py:120-219 for the same seed: R history, jump count, final state"""
+    from scpn_quantum_control_b200.tensor_jump import mcwf_ensemble, mcwf_trajectory
+
+    K = oc.paper27_K(16)[:n, :n] * 1.5
+    w = oc.OMEGA_N_16[:n]
+    t_max, dt = (1.0, 0.1) if n < 13 else (0.3, 0.1)
+    got = mcwf_trajectory(K, w, gamma_amp, gamma_deph, t_max, dt, seed)
+    want = on.mcwf_trajectory(K, w, gamma_amp, gamma_deph, t_max, dt, seed)
+    assert got["n_jumps"] == want["n_jumps"]
+    assert np.abs(got["R"] - want["R"]).max() < R_TOL
+    assert 1.0 - oc.fidelity(got["psi_final"], want["psi_final"]) < FID_TOL
+    if n == 4:
+        ens = mcwf_ensemble(K, w, gamma_amp, gamma_deph, 0.5, 0.1, n_trajectories=3, seed=5)
+        seeds = np.random.default_rng(5).integers(0, 2**31, size=3)
+        ref = np.array([on.mcwf_trajectory(K, w, gamma_amp, gamma_deph, 0.5, 0.1, int(sd))["R"] for sd in seeds])
+        assert np.abs(ens["R_trajectories"] - ref).max() < R_TOL
+        assert np.abs(ens["R_mean"] - ref.mean(axis=0)).max() < R_TOL and ens["n_trajectories"] == 3

@@ -132,3 +132,95 @@ def test_next_rows_oracle_reproduces_the_committed_vectors():
                            f["steps_per_period"])
     assert np.abs(fl["R_values"] - np.array(f["R_values"])).max() < 1e-12
     assert fl["subharmonic_ratio"] == pytest.approx(f["subharmonic_ratio"], rel=1e-9)
+
+
+class _NumpyDevice:
+    """NumPy twin of tensor_jump._Device (same methods, little-endian index bits like the engine): lets the trajectory logic
+    of the product module run on the CPU against the oracle's literal restatement of the reference."""
+
+    def __init__(self, n, K, omega):
+        self.n = n
+        Ks = (K + K.T) / 2.0
+        self.H = oc.hamiltonian_sparse(Ks, omega)
+        self.psi = None
+
+    def prepare(self, angles):
+        psi = np.ones(1, dtype=np.complex128)
+        for q in range(self.n):   # bit q = qubit q: later factors are less significant in np.kron -> build from the top
+            psi = np.kron(np.array([np.cos(angles[q] / 2), np.sin(angles[q] / 2)], dtype=np.complex128), psi)
+        self.psi = psi
+
+    def exact_step(self, step_dt, n_steps):
+        self.psi = oc.exact_step(self.psi, self.H, step_dt)
+
+    def decay(self, rate_zero, scale):
+        idx = np.arange(self.psi.shape[0])
+        ones = np.array([bin(int(k)).count("1") for k in idx])
+        self.psi = self.psi * (scale * np.exp(-rate_zero * (self.n - ones)))
+
+    def jump(self, bit, kind):
+        idx = np.arange(self.psi.shape[0])
+        m = 1 << bit
+        if kind == 0:
+            out = np.zeros_like(self.psi)
+            lower = idx[(idx & m) == 0]
+            out[lower | m] = self.psi[lower]
+            self.psi = out
+        else:
+            self.psi = np.where(idx & m, -self.psi, self.psi)
+
+    def norm2(self):
+        return float(np.vdot(self.psi, self.psi).real)
+
+    def z_expectations(self):
+        return oc.z_expectations(self.psi, self.n)
+
+    def xy_sum(self):
+        ex, ey = oc.xy_expectations(self.psi, self.n)
+        return complex(ex.sum(), ey.sum())
+
+    def snapshot(self):
+        return self.psi.copy()
+
+    def restore(self, snap):
+        self.psi = snap.copy()
+
+    def state(self):
+        return self.psi.copy()
+
+
+@pytest.mark.parametrize("n,gamma_amp,gamma_deph,seed", [(3, 0.9, 0.0, 1), (4, 0.6, 0.4, 7), (5, 0.0, 1.2, 3), (4, 0.0, 0.0, 5), (5, 1.5, 0.5, 11)])
+def test_mcwf_trajectory_logic_vs_oracle(n, gamma_amp, gamma_deph, seed):
+    """tensor_jump._run_trajectory (factorised step: exact unitary step, bit-count damping, jump kernels on index bit
+    n-1-i) on the NumPy device twin == the oracle's literal restatement of the reference (sparse H_eff, Kronecker-order
+    operators): same R history, same jumps, same final state"""
+    from scpn_quantum_control_b200 import tensor_jump as tj
+
+    K = oc.paper27_K(16)[:n, :n] * 1.5
+    w = oc.OMEGA_N_16[:n]
+    want = on.mcwf_trajectory(K, w, gamma_amp, gamma_deph, 1.0, 0.1, seed)
+    got = tj._run_trajectory(_NumpyDevice(n, K, w), n, w, gamma_amp, gamma_deph, 1.0, 0.1, np.random.default_rng(seed))
+    assert got["n_jumps"] == want["n_jumps"]
+    assert np.abs(got["R"] - want["R"]).max() < 1e-9
+    assert 1 - oc.fidelity(got["psi_final"], want["psi_final"]) < 1e-9
+    assert np.allclose(got["times"], want["times"])
+    if gamma_amp + gamma_deph >= 0.9:
+        assert want["n_jumps"] > 0, "the parameters are meant to exercise the jump branch"
+
+
+def test_mcwf_validation_messages():
+    from scpn_quantum_control_b200.tensor_jump import mcwf_ensemble, mcwf_trajectory
+
+    K, w = oc.paper27_K(4), oc.OMEGA_N_16[:4]
+    with pytest.raises(ValueError, match="K must be a square two-dimensional coupling matrix."):
+        mcwf_trajectory(K[:3], w)
+    with pytest.raises(ValueError, match="omega must be a one-dimensional vector matching K."):
+        mcwf_trajectory(K, w[:3])
+    with pytest.raises(ValueError, match="gamma_amp must be finite and non-negative."):
+        mcwf_trajectory(K, w, gamma_amp=-1.0)
+    with pytest.raises(ValueError, match="dt must be finite and positive."):
+        mcwf_trajectory(K, w, dt=0.0)
+    with pytest.raises(ValueError, match="n_trajectories must be a positive integer."):
+        mcwf_ensemble(K, w, n_trajectories=True)
+    with pytest.raises(ValueError, match="n_trajectories must be at least 1."):
+        mcwf_ensemble(K, w, n_trajectories=0)
