@@ -411,7 +411,10 @@ void fill_desc(xyk_handle h, Program& prog, const std::vector<int>& loc2log, con
         }
         void* dtab = nullptr;
         if (nhi - d.ph_b1 > kPhTabBits || cudaMalloc(&dtab, tab.size() * sizeof(double2)) != cudaSuccess ||
-            cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess) {
+            // stream-ordered upload (a plain cudaMemcpy from pageable memory may return before its DMA has landed, and the
+            // engine's stream does not wait for the legacy stream)
+            cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+            cudaStreamSynchronize(h->stream) != cudaSuccess) {
             if (dtab) cudaFree(dtab);
             d.flags &= ~kPassHasPhase;  // falls back to the separate phase sweep (run_passes)
         } else {
@@ -1216,7 +1219,8 @@ int xyk_set_problem_xxz(xyk_handle h, const double* K, const double* omega, doub
     std::vector<double> J(h->Ksym);
     for (double& v : J) v *= delta;
     XYK_CUDA(h, cudaStreamSynchronize(h->stream));  // a ZZ sweep in flight still reads the previous table
-    XYK_CUDA(h, cudaMemcpy(h->d_J, J.data(), sizeof(double) * J.size(), cudaMemcpyHostToDevice));
+    XYK_CUDA(h, cudaMemcpyAsync(h->d_J, J.data(), sizeof(double) * J.size(), cudaMemcpyHostToDevice, h->stream));   // stream-ordered
+    XYK_CUDA(h, cudaStreamSynchronize(h->stream));   // J is a local vector
     h->zz_delta = delta;
     return XYK_OK;
 }
@@ -1586,7 +1590,9 @@ int xyk_apply_occupation_decay(xyk_handle h, double rate_zero, double rate_one, 
             const int ones = __builtin_popcount((unsigned)v), zeros = (hi[c] - lo[c]) - ones;
             tab[(size_t)c * kTabStride + v] = make_double2((c == 0 ? scale : 1.0) * std::exp(-rate_zero * zeros - rate_one * ones), 0.0);
         }
-    XYK_CUDA(h, cudaMemcpy(h->d_tab, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
+    // stream-ordered upload: a plain cudaMemcpy from pageable memory may return before its DMA has landed, and the engine's
+    // stream is non-blocking (it does not wait for the legacy stream) -- the kernel below would read the previous table
+    XYK_CUDA(h, cudaMemcpyAsync(h->d_tab, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice, h->stream));
     const uint64_t dim = 1ull << nl;
     if (h->dtype == 0)
         phase_apply_kernel<double><<<grid_for(h, dim, 256), 256, 0, h->stream>>>((double2*)h->buf[h->cur], h->d_tab, kTabStride, nl, b1, b2);
