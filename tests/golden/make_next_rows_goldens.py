@@ -47,6 +47,12 @@ def main() -> None:
                          "drive_frequency": 2.0, "n_periods": 2, "steps_per_period": 8, "times": fl["times"].tolist(),
                          "R_values": fl["R_values"].tolist(), "drive_signal": fl["drive_signal"].tolist(),
                          "subharmonic_ratio": fl["subharmonic_ratio"]}
+    n = 4
+    K = oc.paper27_K(16)[:n, :n] * 1.5
+    tr = on.mcwf_trajectory(K, oc.OMEGA_N_16[:n], 0.6, 0.4, 1.0, 0.1, 7)
+    out["mcwf_n4_seed7"] = {"K": "1.5 * paper27_K(16)[:4, :4]", "omega": "OMEGA_N_16[:4]", "gamma_amp": 0.6, "gamma_deph": 0.4,
+                            "t_max": 1.0, "dt": 0.1, "seed": 7, "R": tr["R"].tolist(), "n_jumps": tr["n_jumps"],
+                            "psi_final_re": tr["psi_final"].real.tolist(), "psi_final_im": tr["psi_final"].imag.tolist()}
     (HERE / "next_rows_vectors.json").write_text(json.dumps(out, indent=1))
     print("wrote", HERE / "next_rows_vectors.json")
 

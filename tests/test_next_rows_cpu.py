@@ -224,3 +224,17 @@ def test_mcwf_validation_messages():
         mcwf_ensemble(K, w, n_trajectories=True)
     with pytest.raises(ValueError, match="n_trajectories must be at least 1."):
         mcwf_ensemble(K, w, n_trajectories=0)
+
+
+def test_mcwf_oracle_and_trajectory_logic_reproduce_the_committed_vector():
+    from scpn_quantum_control_b200 import tensor_jump as tj
+
+    m = _next_rows_goldens()["mcwf_n4_seed7"]
+    K, w = oc.paper27_K(16)[:4, :4] * 1.5, oc.OMEGA_N_16[:4]
+    want_psi = np.array(m["psi_final_re"]) + 1j * np.array(m["psi_final_im"])
+    tr = on.mcwf_trajectory(K, w, m["gamma_amp"], m["gamma_deph"], m["t_max"], m["dt"], m["seed"])
+    assert tr["n_jumps"] == m["n_jumps"] and np.abs(tr["R"] - np.array(m["R"])).max() < 1e-12
+    got = tj._run_trajectory(_NumpyDevice(4, K, w), 4, w, m["gamma_amp"], m["gamma_deph"], m["t_max"], m["dt"],
+                             np.random.default_rng(m["seed"]))
+    assert got["n_jumps"] == m["n_jumps"] and np.abs(got["R"] - np.array(m["R"])).max() < 1e-9
+    assert 1 - oc.fidelity(got["psi_final"], want_psi) < 1e-9
