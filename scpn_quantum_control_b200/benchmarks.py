@@ -14,6 +14,7 @@ The classical rows of those artefacts (SciPy ODE, dense expm) stay in the refere
 
 from __future__ import annotations
 
+import platform
 import time
 from dataclasses import dataclass
 from typing import Any
@@ -139,9 +140,12 @@ def statevector_scaling_row(n_qubits: int, max_statevector_qubits: int | None = 
     |0...0> evolved by ``evolve(0.1, trotter_steps=1)`` of the Paper-27 problem (omega = linspace(0.1, 1, n) above 16
     qubits, :121-126), then (R, psi).  ``max_statevector_qubits`` defaults to the device-memory budget."""
     limit = statevector_qubit_budget(device=device) if max_statevector_qubits is None else max_statevector_qubits
-    row: dict[str, Any] = {"n_qubits": n_qubits, "baseline": "gpu_statevector", "status": "ok", "skip_reasons": []}
+    # the measurement's share of the reference's row schema (_base_row, :93-108); protocol id, command, dependency versions and
+    # git commit are provenance fields the campaign script adds around it
+    row: dict[str, Any] = {"n_qubits": n_qubits, "baseline": "gpu_statevector", "status": "ok", "wall_time_ms": None,
+                           "memory_bytes": None, "metric_payload": {}, "machine": platform.platform(), "notes": []}
     if n_qubits > limit:
-        row.update(status="skipped", skip_reasons=["size gate"])
+        row.update(status="skipped", notes=["size gate"])
         return row
     k_matrix = build_knm_paper27(n_qubits)
     omega = OMEGA_N_16[:n_qubits].copy() if n_qubits <= OMEGA_N_16.size else np.linspace(0.1, 1.0, n_qubits)

@@ -86,8 +86,9 @@ def test_benchmark_caller_shims_validate_like_the_reference():
         bm.quantum_trotter_row(4, trotter_per_step=0)
     row = bm.ComparisonMethodRow("quantum_trotter", "x", False, None, None, 0.0, "why")
     assert row.to_dict()["unavailable_reason"] == "why" and list(row.to_dict())[0] == "method"
-    assert bm.statevector_scaling_row(20, max_statevector_qubits=16) == {
-        "n_qubits": 20, "baseline": "gpu_statevector", "status": "skipped", "skip_reasons": ["size gate"]}
+    skipped = bm.statevector_scaling_row(20, max_statevector_qubits=16)
+    assert skipped["status"] == "skipped" and skipped["notes"] == ["size gate"] and skipped["n_qubits"] == 20
+    assert {"baseline", "wall_time_ms", "memory_bytes", "metric_payload", "machine"} <= set(skipped)   # the reference's row schema
 
 
 def test_solver_rejects_bad_next_row_arguments():
