@@ -124,6 +124,15 @@ def simulate_execute(simulate_spec: dict[str, Any], *, backend: str = "gpu_state
         "dt": simulate_spec["dt"],
         "trotter_per_step": simulate_spec["trotter_per_step"],
         "trotter_order": simulate_spec["trotter_order"],
+        # the reference's summary keys (:210-224)
+        "evolution_schema": "studio.quantum-evolution.v1",   # studio/verbs.py:47 QUANTUM_EVOLUTION_SCHEMA
+        "n_points": int(times.shape[0]),
+        "order_parameter_initial": float(order_parameter[0]),
+        "order_parameter_final": float(order_parameter[-1]),
+        "order_parameter_max": float(order_parameter.max()),
+        "order_parameter_mean": float(order_parameter.mean()),
+        "order_parameter_delta": float(order_parameter[-1] - order_parameter[0]),
+        # plus the trajectory itself
         "n_time_points": int(times.size),
         "times": times.tolist(),
         "R": order_parameter.tolist(),
